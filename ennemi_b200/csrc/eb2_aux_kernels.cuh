@@ -1,0 +1,194 @@
+// ennemi_b200 — non-templated kernels: 1-D marginal search, digamma reduction, layout helpers.
+// Included by eb2_lib.cu only (one definition per library).
+#pragma once
+#include "eb2_kernels.cuh"
+
+namespace eb2 {
+
+// ----------------------------------------------------------------------------------------------
+// (2a) 1-D marginal counts: binary search in an ascending coordinate array with the EXACT
+//      predicate |fl(x_i - s_j)| <= r_i (rounded subtraction is monotone in s_j, so the predicate
+//      is monotone on each side of x_i and the count equals what the all-pairs test would give).
+// ----------------------------------------------------------------------------------------------
+struct SearchArgs {
+  const double* qcoord;   // query coordinate per query slot
+  const double* radius;   // per query slot
+  const double* sorted;   // ascending candidate coordinates
+  const Tile* tiles;      // q_lo/q_n: query slots; c_lo/c_len: slice of `sorted` to search
+  int ntiles;
+  int* cnt;               // out per query slot
+};
+
+__global__ void __launch_bounds__(kThreads) search_kernel(const SearchArgs a) {
+  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = a.tiles[tile_id];
+    const double* s = a.sorted + tile.c_lo;
+    for (int qi = threadIdx.x; qi < tile.q_n; qi += kThreads) {
+      const int slot = tile.q_lo + qi;
+      const double x = a.qcoord[slot];
+      const double r = a.radius[slot];
+      // first j with fl(x - s_j) <= r   (x - s_j is non-increasing in j)
+      int lo = 0, hi = tile.c_len;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((x - s[mid]) <= r) hi = mid; else lo = mid + 1;
+      }
+      const int first = lo;
+      // first j with fl(s_j - x) > r    (s_j - x is non-decreasing in j)
+      lo = 0; hi = tile.c_len;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((s[mid] - x) > r) hi = mid; else lo = mid + 1;
+      }
+      a.cnt[slot] = max(0, lo - first);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// (3) digamma terms + deterministic reduction
+// ----------------------------------------------------------------------------------------------
+enum PsiMode { PSI_A = 1, PSI_AB = 2, PSI_AB_MINUS_C = 3, LOG_DIST = 4 };
+
+struct PsiArgs {
+  const int* cnt_a;
+  const int* cnt_b;
+  const int* cnt_c;
+  const double* dist;     // LOG_DIST mode
+  const Tile* tiles;
+  int ntiles;
+  int mode;
+  double* partial;        // [ntiles][4]: sum, zeros_a, zeros_b, zeros_c
+};
+
+__global__ void __launch_bounds__(kThreads) psi_kernel(const PsiArgs a) {
+  __shared__ double red[kThreads / 32];
+  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = a.tiles[tile_id];
+    double sum = 0.0, za = 0.0, zb = 0.0, zc = 0.0;
+#pragma unroll
+    for (int i = 0; i < kQpt; ++i) {
+      const int qi = threadIdx.x + i * kThreads;
+      if (qi < tile.q_n) {
+        const int slot = tile.q_lo + qi;
+        if (a.mode == LOG_DIST) {
+          sum += log(a.dist[slot]);
+        } else {
+          // a zero count makes the reference's _psi return a scalar +inf (:338-339); it is reported
+          // through the zero counters and contributes nothing to the finite sum.
+          const int na = a.cnt_a[slot];
+          double term = 0.0;
+          if (na == 0) za += 1.0; else term = psi_ref((double)na);
+          if (a.mode >= PSI_AB) {
+            const int nb = a.cnt_b[slot];
+            if (nb == 0) zb += 1.0; else term = term + psi_ref((double)nb);
+          }
+          if (a.mode == PSI_AB_MINUS_C) {
+            const int nc = a.cnt_c[slot];
+            if (nc == 0) zc += 1.0; else term = term - psi_ref((double)nc);
+          }
+          sum += term;
+        }
+      }
+    }
+    sum = block_sum<kThreads>(sum, red);
+    za = block_sum<kThreads>(za, red);
+    zb = block_sum<kThreads>(zb, red);
+    zc = block_sum<kThreads>(zc, red);
+    if (threadIdx.x == 0) {
+      double* p = a.partial + (int64_t)tile_id * 4;
+      p[0] = sum; p[1] = za; p[2] = zb; p[3] = zc;
+    }
+  }
+}
+
+// one CTA folds the per-tile partials in a fixed order: thread t sums tiles t, t+256, ... then the tree
+__global__ void __launch_bounds__(kThreads) psi_final_kernel(const double* partial, int ntiles, double* out /*4*/) {
+  __shared__ double red[kThreads / 32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int t = threadIdx.x; t < ntiles; t += kThreads) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] += partial[(int64_t)t * 4 + c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double r = block_sum<kThreads>(acc[c], red);
+    if (threadIdx.x == 0) out[c] = r;
+  }
+}
+
+// psi of a plain count array (eb2_psi)
+__global__ void psi_array_kernel(const long long* counts, int64_t n, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const long long c = counts[i];
+    out[i] = c == 0 ? __longlong_as_double(0x7ff0000000000000LL) : psi_ref((double)c);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// layout helpers
+// ----------------------------------------------------------------------------------------------
+__global__ void iota_kernel(int* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+// rank -> padded slot.  Unsegmented: slot = rank.  Segmented: ranks are class-major, class c owns
+// ranks [seg_rank[c], seg_rank[c+1]) and slots starting at seg_slot[c].
+struct GatherArgs {
+  const double* raw;      // d x n dimension-major input
+  int64_t n;
+  int d;
+  const int* perm;        // rank -> input row (NULL: identity)
+  const int* cls_sorted;  // class of each rank (NULL: one segment)
+  const int* seg_rank;    // per class
+  const int* seg_slot;    // per class
+  double* P;              // d x stride, pre-filled with NaN
+  int64_t stride;
+  int* slot_row;          // slot -> input row, pre-filled with -1
+};
+
+__global__ void gather_kernel(const GatherArgs a) {
+  const int64_t rank = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= a.n) return;
+  const int row = a.perm ? a.perm[rank] : (int)rank;
+  int64_t slot = rank;
+  if (a.cls_sorted) {
+    const int c = a.cls_sorted[rank];
+    slot = a.seg_slot[c] + (rank - a.seg_rank[c]);
+  }
+  for (int t = 0; t < a.d; ++t) a.P[t * a.stride + slot] = a.raw[t * a.n + row];
+  a.slot_row[slot] = row;
+}
+
+__global__ void gather_int_kernel(const int* src, const int* perm, int* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+
+__global__ void radius_kernel(const double* eps, double* radius, int64_t nslots) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nslots) radius[i] = eps[i] - 1e-12;   // _entropy_estimators.py:109
+}
+
+// slot-order results -> caller's row order
+__global__ void scatter_f64_kernel(const double* src, const int* slot_row, int64_t nslots, double* dst) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nslots) { const int r = slot_row[s]; if (r >= 0) dst[r] = src[s]; }
+}
+__global__ void scatter_i64_kernel(const int* src, const int* slot_row, int64_t nslots, long long* dst) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nslots) { const int r = slot_row[s]; if (r >= 0) dst[r] = (long long)src[s]; }
+}
+
+// 1 if any of the first `count` values is NaN or +-inf
+__global__ void nonfinite_kernel(const double* v, int64_t count, int* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const double x = v[i];
+    if (!(fabs(x) < __longlong_as_double(0x7ff0000000000000LL))) *flag = 1;
+  }
+}
+
+}  // namespace eb2

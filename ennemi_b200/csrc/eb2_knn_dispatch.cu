@@ -1,0 +1,39 @@
+// ennemi_b200 — instantiations of knn_kernel<D, K1T>.
+#include "eb2_launch.h"
+
+namespace eb2 {
+
+int knn_grid(int k, int ntiles, int sm_count) {
+  if (k + 1 <= 8) return ntiles;                 // one CTA per query tile, hardware scheduler balances
+  const int cap = sm_count * 2;                  // heap variant is persistent: scratch is per CTA
+  return ntiles < cap ? ntiles : cap;
+}
+
+template <int D>
+static cudaError_t launch_d(const KnnArgs& a, int grid, cudaStream_t s) {
+  const int k1 = a.k + 1;
+  if (k1 <= 4) knn_kernel<D, 4><<<grid, kThreads, 0, s>>>(a);
+  else if (k1 <= 8) knn_kernel<D, 8><<<grid, kThreads, 0, s>>>(a);
+  else knn_kernel<D, 0><<<grid, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn(int D, const KnnArgs& a, int grid, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_d<1>(a, grid, s);
+    case 2: return launch_d<2>(a, grid, s);
+    case 3: return launch_d<3>(a, grid, s);
+    case 4: return launch_d<4>(a, grid, s);
+    case 5: return launch_d<5>(a, grid, s);
+    case 6: return launch_d<6>(a, grid, s);
+    case 7: return launch_d<7>(a, grid, s);
+    case 8: return launch_d<8>(a, grid, s);
+    case 9: return launch_d<9>(a, grid, s);
+    case 10: return launch_d<10>(a, grid, s);
+    case 11: return launch_d<11>(a, grid, s);
+    case 12: return launch_d<12>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace eb2

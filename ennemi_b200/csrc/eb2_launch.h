@@ -1,0 +1,13 @@
+// ennemi_b200 — host-side launchers of the templated kernels (one translation unit each so the
+// instantiations build in parallel).
+#pragma once
+#include "eb2_kernels.cuh"
+
+namespace eb2 {
+// D = dimension of the search space (1..kMaxDim); k+1 <= 8 uses the register top-k variants,
+// larger k the heap variant (args.heap must then hold (k+1) * grid * kTileQ doubles).
+cudaError_t launch_knn(int D, const KnnArgs& args, int grid, cudaStream_t stream);
+int knn_grid(int k, int ntiles, int sm_count);
+// C shared + E private coordinates
+cudaError_t launch_count(int C, int E, const CountArgs& args, int grid, cudaStream_t stream);
+}  // namespace eb2

@@ -1,0 +1,904 @@
+// ennemi_b200 — C ABI, per-device contexts and the orchestration of the hot path (sm_100a).
+//
+// Data layout in HBM (per call, on the device's stream, from the stream-ordered pool):
+//   raw     d x n           dimension-major copy of the caller's coordinates
+//   P       d x stride      "point set": the same rows permuted into processing order and padded
+//                           with NaN; rows of one class form a segment that starts on a 16-slot
+//                           boundary (TMA bulk copies need 16 B alignment); inside a segment the
+//                           rows are ascending in one chosen coordinate (`sort_row`), which is what
+//                           lets the all-pairs kernels skip candidate chunks exactly
+//   slot_row  stride        slot -> caller's row (-1 for padding)
+//   eps, radius, counts     per slot
+//   tiles                   one entry per 512-row query tile: query slots + candidate segment
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ennemi_b200.h"
+#include "eb2_aux_kernels.cuh"
+#include "eb2_launch.h"
+
+namespace {
+
+using namespace eb2;
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+struct CudaFail {
+  cudaError_t e;
+  const char* what;
+  int line;
+};
+#define CU(x)                                            \
+  do {                                                   \
+    cudaError_t e_ = (x);                                \
+    if (e_ != cudaSuccess) throw CudaFail{e_, #x, __LINE__}; \
+  } while (0)
+
+constexpr int kMaxDev = 64;
+constexpr int kNumEvents = 8;
+
+struct Ctx {
+  int dev = -1;
+  bool ready = false;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[kNumEvents] = {};
+  int sm_count = 148;
+  char* pinned = nullptr;   // host staging: tile tables up, results down
+  size_t pinned_cap = 0;
+  double last_ms[5] = {0, 0, 0, 0, 0};
+  int last_launches = 0;
+};
+
+Ctx g_ctx[kMaxDev];
+std::mutex g_init_mu;
+
+Ctx& get_ctx(int dev) {
+  if (dev < 0 || dev >= kMaxDev) throw CudaFail{cudaErrorInvalidDevice, "device index", __LINE__};
+  Ctx& c = g_ctx[dev];
+  if (c.ready) return c;
+  std::lock_guard<std::mutex> g(g_init_mu);
+  if (c.ready) return c;
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (dev >= count) throw CudaFail{cudaErrorInvalidDevice, "device index beyond cudaGetDeviceCount", __LINE__};
+  CU(cudaSetDevice(dev));
+  CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  for (auto& e : c.ev) CU(cudaEventCreate(&e));
+  CU(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t keep = std::numeric_limits<uint64_t>::max();   // keep freed workspace cached in the pool
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  c.pinned_cap = 4 << 20;
+  CU(cudaMallocHost(reinterpret_cast<void**>(&c.pinned), c.pinned_cap));
+  c.dev = dev;
+  c.ready = true;
+  return c;
+}
+
+// Per-call scratch: stream-ordered allocations, released when the call ends.
+struct Scratch {
+  Ctx& c;
+  std::vector<void*> ptrs;
+  size_t pinned_used = 0;
+  int launches = 0;
+  explicit Scratch(Ctx& ctx) : c(ctx) {}
+  std::vector<void*> extra_pinned;
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, c.stream);
+    if (!extra_pinned.empty()) {
+      cudaStreamSynchronize(c.stream);
+      for (void* p : extra_pinned) cudaFreeHost(p);
+    }
+  }
+  template <typename T>
+  T* dev(size_t count) {
+    void* p = nullptr;
+    CU(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), c.stream));
+    ptrs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  // pinned staging slice (valid until the call ends)
+  template <typename T>
+  T* host(size_t count) {
+    const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    if (pinned_used + bytes > c.pinned_cap) {
+      void* extra = nullptr;                       // rare: a dedicated block for this call
+      CU(cudaMallocHost(&extra, bytes));
+      extra_pinned.push_back(extra);
+      return static_cast<T*>(extra);
+    }
+    T* p = reinterpret_cast<T*>(c.pinned + pinned_used);
+    pinned_used += bytes;
+    return p;
+  }
+};
+
+inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- the point set -----------------------------------------------------------------------------
+struct PointSet {
+  double* P = nullptr;
+  int64_t stride = 0;
+  int d = 0;
+  int64_t n = 0;
+  int* slot_row = nullptr;
+  int sort_row = -1;
+  std::vector<int> seg_slot, seg_len;   // per segment
+};
+
+template <typename K, typename V>
+void sort_pairs(Scratch& s, const K* kin, K* kout, const V* vin, V* vout, int n, int begin_bit, int end_bit) {
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin, kout, vin, vout, n, begin_bit, end_bit, s.c.stream));
+  void* tmp = s.dev<char>(tmp_bytes);
+  CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, n, begin_bit, end_bit, s.c.stream));
+}
+
+void sort_keys(Scratch& s, const double* kin, double* kout, int n) {
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kin, kout, n, 0, 64, s.c.stream));
+  void* tmp = s.dev<char>(tmp_bytes);
+  CU(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, kin, kout, n, 0, 64, s.c.stream));
+}
+
+// raw: d x n on the device.  cls: class id per row on the device (or NULL), class_size: rows per class.
+PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const int* cls,
+                         const std::vector<int>& class_size, int sort_row) {
+  cudaStream_t st = s.c.stream;
+  PointSet ps;
+  ps.d = d;
+  ps.n = n;
+  ps.sort_row = sort_row;
+  const int nseg = cls ? static_cast<int>(class_size.size()) : 1;
+  std::vector<int> seg_rank(nseg);
+  ps.seg_slot.resize(nseg);
+  ps.seg_len.resize(nseg);
+  int64_t rank = 0, slot = 0;
+  for (int c = 0; c < nseg; ++c) {
+    const int len = cls ? class_size[c] : static_cast<int>(n);
+    seg_rank[c] = static_cast<int>(rank);
+    ps.seg_slot[c] = static_cast<int>(slot);
+    ps.seg_len[c] = len;
+    rank += len;
+    slot += round_up(len, kSegAlign);
+  }
+  ps.stride = std::max<int64_t>(slot, kSegAlign);
+  const int blocks_n = cdiv(n, 256);
+
+  // rank -> input row
+  const int* perm = nullptr;
+  const int* cls_sorted = nullptr;
+  if (sort_row >= 0) {
+    int* iota = s.dev<int>(n);
+    iota_kernel<<<blocks_n, 256, 0, st>>>(iota, static_cast<int>(n));
+    s.launches++;
+    double* keys_out = s.dev<double>(n);
+    int* p1 = s.dev<int>(n);
+    sort_pairs<double, int>(s, raw + static_cast<int64_t>(sort_row) * n, keys_out, iota, p1, static_cast<int>(n), 0, 64);
+    perm = p1;
+    if (cls) {
+      // stable second pass by class keeps the coordinate order inside each class
+      int* cls_by_rank = s.dev<int>(n);
+      gather_int_kernel<<<blocks_n, 256, 0, st>>>(cls, p1, cls_by_rank, static_cast<int>(n));
+      s.launches++;
+      int* cls_out = s.dev<int>(n);
+      int* p2 = s.dev<int>(n);
+      int bits = 1;
+      while ((1 << bits) < nseg && bits < 31) ++bits;
+      sort_pairs<int, int>(s, cls_by_rank, cls_out, p1, p2, static_cast<int>(n), 0, bits);
+      perm = p2;
+      cls_sorted = cls_out;
+    }
+  } else if (cls) {
+    int* iota = s.dev<int>(n);
+    iota_kernel<<<blocks_n, 256, 0, st>>>(iota, static_cast<int>(n));
+    s.launches++;
+    int* cls_out = s.dev<int>(n);
+    int* p2 = s.dev<int>(n);
+    int bits = 1;
+    while ((1 << bits) < nseg && bits < 31) ++bits;
+    sort_pairs<int, int>(s, cls, cls_out, iota, p2, static_cast<int>(n), 0, bits);
+    perm = p2;
+    cls_sorted = cls_out;
+  }
+
+  ps.P = s.dev<double>(static_cast<size_t>(d) * ps.stride);
+  ps.slot_row = s.dev<int>(ps.stride);
+  CU(cudaMemsetAsync(ps.P, 0xFF, sizeof(double) * d * ps.stride, st));     // all-ones = NaN
+  CU(cudaMemsetAsync(ps.slot_row, 0xFF, sizeof(int) * ps.stride, st));     // -1
+  GatherArgs ga;
+  ga.raw = raw; ga.n = n; ga.d = d; ga.perm = perm; ga.cls_sorted = cls_sorted;
+  ga.seg_rank = nullptr; ga.seg_slot = nullptr;
+  if (cls) {
+    int* h = s.host<int>(2 * nseg);
+    std::memcpy(h, seg_rank.data(), sizeof(int) * nseg);
+    std::memcpy(h + nseg, ps.seg_slot.data(), sizeof(int) * nseg);
+    int* dv = s.dev<int>(2 * nseg);
+    CU(cudaMemcpyAsync(dv, h, sizeof(int) * 2 * nseg, cudaMemcpyHostToDevice, st));
+    ga.seg_rank = dv;
+    ga.seg_slot = dv + nseg;
+  }
+  ga.P = ps.P; ga.stride = ps.stride; ga.slot_row = ps.slot_row;
+  gather_kernel<<<blocks_n, 256, 0, st>>>(ga);
+  s.launches++;
+  CU(cudaGetLastError());
+  return ps;
+}
+
+// Query tiles of a point set whose first row rank lies in [row_lo, row_hi); the candidate segment
+// is the tile's own segment (self) or a fixed slice (c_lo, c_len) of another array.
+struct TileSet {
+  Tile* dev = nullptr;
+  int count = 0;
+  int64_t rows = 0;
+};
+
+TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_hi, bool self, int c_lo, int c_len) {
+  std::vector<Tile> t;
+  int64_t rank = 0, rows = 0;
+  for (size_t g = 0; g < ps.seg_slot.size(); ++g) {
+    for (int off = 0; off < ps.seg_len[g]; off += kTileQ) {
+      const int qn = std::min(kTileQ, ps.seg_len[g] - off);
+      if (rank >= row_lo && rank < row_hi) {
+        Tile x;
+        x.q_lo = ps.seg_slot[g] + off;
+        x.q_n = qn;
+        x.c_lo = self ? ps.seg_slot[g] : c_lo;
+        x.c_len = self ? ps.seg_len[g] : c_len;
+        t.push_back(x);
+        rows += qn;
+      }
+      rank += qn;
+    }
+  }
+  TileSet ts;
+  ts.count = static_cast<int>(t.size());
+  ts.rows = rows;
+  if (ts.count) {
+    Tile* h = s.host<Tile>(t.size());
+    std::memcpy(h, t.data(), sizeof(Tile) * t.size());
+    ts.dev = s.dev<Tile>(t.size());
+    CU(cudaMemcpyAsync(ts.dev, h, sizeof(Tile) * t.size(), cudaMemcpyHostToDevice, s.c.stream));
+  }
+  return ts;
+}
+
+RowSel rows_range(int first, int count) {
+  RowSel r{};
+  for (int t = 0; t < count; ++t) r.row[t] = first + t;
+  return r;
+}
+
+void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, const TileSet& ts, double* eps,
+             unsigned long long* pairs) {
+  if (!ts.count) return;
+  KnnArgs a;
+  a.P = ps.P; a.stride = ps.stride; a.rows = rows; a.tiles = ts.dev; a.k = k;
+  a.sort_row = ps.sort_row; a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
+  const int grid = knn_grid(k, ts.count, s.c.sm_count);
+  if (k + 1 > 8) a.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * kTileQ);
+  CU(launch_knn(D, a, grid, s.c.stream));
+  s.launches++;
+}
+
+struct CountOut {
+  int* s = nullptr;
+  int* e0 = nullptr;
+  int* e1 = nullptr;
+};
+
+// queries from `qs` (tiles), candidates from `bs`; shared rows / extra rows are given per set
+void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E, const RowSel& q_srow,
+               const RowSel& b_srow, const RowSel& q_erow, const RowSel& b_erow, const double* radius,
+               const TileSet& ts, bool prune, const CountOut& out, unsigned long long* pairs) {
+  if (!ts.count) return;
+  CountArgs a;
+  a.Q = qs.P; a.qstride = qs.stride; a.B = bs.P; a.bstride = bs.stride;
+  a.q_srow = q_srow; a.b_srow = b_srow; a.q_erow = q_erow; a.b_erow = b_erow;
+  a.radius = radius; a.tiles = ts.dev; a.ntiles = ts.count;
+  a.prune_q_row = -1; a.prune_b_row = -1;
+  if (prune && bs.sort_row >= 0) {
+    // the sorted coordinate of the candidate set must be one of the coordinates of the marginal
+    for (int t = 0; t < C; ++t)
+      if (b_srow.row[t] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_srow.row[t]; }
+    if (C == 0 && E == 1 && b_erow.row[0] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_erow.row[0]; }
+  }
+  a.cnt_s = out.s; a.cnt_e0 = out.e0; a.cnt_e1 = out.e1; a.pairs = pairs;
+  CU(launch_count(C, E, a, ts.count, s.c.stream));
+  s.launches++;
+}
+
+void run_search(Scratch& s, const double* qcoord, const double* radius, const double* sorted, const TileSet& ts, int* cnt) {
+  if (!ts.count) return;
+  SearchArgs a;
+  a.qcoord = qcoord; a.radius = radius; a.sorted = sorted; a.tiles = ts.dev; a.ntiles = ts.count; a.cnt = cnt;
+  search_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(a);
+  CU(cudaGetLastError());
+  s.launches++;
+}
+
+// per-tile digamma partials -> 4 doubles on the device
+double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* cc, const double* dist, const TileSet& ts) {
+  double* out4 = s.dev<double>(4);
+  CU(cudaMemsetAsync(out4, 0, sizeof(double) * 4, s.c.stream));
+  if (!ts.count) return out4;
+  PsiArgs a;
+  a.cnt_a = ca; a.cnt_b = cb; a.cnt_c = cc; a.dist = dist; a.tiles = ts.dev; a.ntiles = ts.count; a.mode = mode;
+  a.partial = s.dev<double>(static_cast<size_t>(ts.count) * 4);
+  psi_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(a);
+  psi_final_kernel<<<1, kThreads, 0, s.c.stream>>>(a.partial, ts.count, out4);
+  CU(cudaGetLastError());
+  s.launches += 2;
+  return out4;
+}
+
+// ---- input staging -------------------------------------------------------------------------------
+const double* stage_coords(Scratch& s, const double* coords, int d, int64_t n, uint32_t flags, int* nonfinite_flag) {
+  const double* raw = coords;
+  if (!(flags & EB2_FLAG_DEVICE_INPUT)) {
+    double* dv = s.dev<double>(static_cast<size_t>(d) * n);
+    CU(cudaMemcpyAsync(dv, coords, sizeof(double) * d * n, cudaMemcpyHostToDevice, s.c.stream));
+    raw = dv;
+  }
+  const int64_t total = static_cast<int64_t>(d) * n;
+  nonfinite_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(raw, total, nonfinite_flag);
+  s.launches++;
+  return raw;
+}
+
+struct Outputs {
+  double* eps = nullptr;     // host, caller's row order
+  int64_t* cnt[3] = {nullptr, nullptr, nullptr};
+};
+
+// copies slot-order results to the caller's arrays (row order)
+void export_outputs(Scratch& s, const PointSet& ps, const double* eps, const int* const cnt[3], const Outputs& o) {
+  cudaStream_t st = s.c.stream;
+  const int blocks = cdiv(ps.stride, 256);
+  if (o.eps) {
+    double* tmp = s.dev<double>(ps.n);
+    CU(cudaMemsetAsync(tmp, 0xFF, sizeof(double) * ps.n, st));
+    scatter_f64_kernel<<<blocks, 256, 0, st>>>(eps, ps.slot_row, ps.stride, tmp);
+    s.launches++;
+    CU(cudaMemcpyAsync(o.eps, tmp, sizeof(double) * ps.n, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (o.cnt[i] && cnt[i]) {
+      long long* tmp = s.dev<long long>(ps.n);
+      CU(cudaMemsetAsync(tmp, 0xFF, sizeof(long long) * ps.n, st));
+      scatter_i64_kernel<<<blocks, 256, 0, st>>>(cnt[i], ps.slot_row, ps.stride, tmp);
+      s.launches++;
+      CU(cudaMemcpyAsync(o.cnt[i], tmp, sizeof(long long) * ps.n, cudaMemcpyDeviceToHost, st));
+    }
+  }
+}
+
+// gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
+int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs, const int* nonfinite, int64_t rows,
+                double* partial) {
+  Ctx& c = s.c;
+  struct Res { double v[4]; unsigned long long pairs; int nonfinite; };
+  Res* h = s.host<Res>(1);
+  CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&h->nonfinite, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaEventRecord(c.ev[5], c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[5])); c.last_ms[0] = ms;
+  CU(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2])); c.last_ms[1] = ms;
+  CU(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3])); c.last_ms[2] = ms;
+  CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
+  CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
+  c.last_launches = s.launches;
+  if (h->nonfinite) return fail(EB2_ERR_NONFINITE, "data must be finite, check for nan or inf values");
+  if (partial) {
+    for (int i = 0; i < EB2_P_LEN; ++i) partial[i] = 0.0;
+    partial[EB2_P_SUM] = h->v[0];
+    partial[EB2_P_ZERO_A] = h->v[1];
+    partial[EB2_P_ZERO_B] = h->v[2];
+    partial[EB2_P_ZERO_C] = h->v[3];
+    partial[EB2_P_ROWS] = static_cast<double>(rows);
+    partial[EB2_P_PAIRS] = static_cast<double>(h->pairs);
+  }
+  return EB2_OK;
+}
+
+struct CallInit {
+  unsigned long long* pairs;
+  int* nonfinite;
+};
+CallInit begin_call(Scratch& s) {
+  Ctx& c = s.c;
+  CU(cudaSetDevice(c.dev));
+  CU(cudaEventRecord(c.ev[0], c.stream));
+  CallInit ci;
+  ci.pairs = s.dev<unsigned long long>(1);
+  ci.nonfinite = s.dev<int>(1);
+  CU(cudaMemsetAsync(ci.pairs, 0, sizeof(unsigned long long), c.stream));
+  CU(cudaMemsetAsync(ci.nonfinite, 0, sizeof(int), c.stream));
+  return ci;
+}
+void mark(Scratch& s, int ev) { CU(cudaEventRecord(s.c.ev[ev], s.c.stream)); }
+
+// host copy of the reference's _psi for scalars (_entropy_estimators.py:327-350)
+double psi_host(double y) {
+  if (y == 0.0) return std::numeric_limits<double>::infinity();
+  if (y == 1.0) return -0.5772156649015331;
+  const double y2 = y * y;
+  return std::log(y) - std::pow(y, -6.0) * (y2 * (y2 * (y / 2 + 1.0 / 12) - 1.0 / 120) + 1.0 / 252);
+}
+
+// mean over rows of (psi(a) + psi(b) - psi(c)) given the finite sum and the zero counters:
+// a zero count anywhere in an array turns that array's psi into a scalar +inf in the reference
+double psi_mean(const double* partial, int64_t n) {
+  const double inf = std::numeric_limits<double>::infinity();
+  const bool za = partial[EB2_P_ZERO_A] > 0, zb = partial[EB2_P_ZERO_B] > 0, zc = partial[EB2_P_ZERO_C] > 0;
+  if (!(za || zb || zc)) return partial[EB2_P_SUM] / static_cast<double>(n);
+  return (za ? inf : 0.0) + (zb ? inf : 0.0) - (zc ? inf : 0.0);   // inf - inf = nan, as numpy gives
+}
+
+int check_common(const double* coords, int64_t n, int d, int k) {
+  if (!coords) return fail(EB2_ERR_ARG, "coords is NULL");
+  if (n <= 0 || n >= (int64_t(1) << 31) - 1024) return fail(EB2_ERR_ARG, "n out of range");
+  if (d < 1) return fail(EB2_ERR_ARG, "dimension must be positive");
+  if (d > EB2_MAX_DIM) return fail(EB2_ERR_UNSUPPORTED, "dimension %d above EB2_MAX_DIM=%d", d, EB2_MAX_DIM);
+  if (k <= 0) return fail(EB2_ERR_ARG, "k must be greater than zero");
+  return EB2_OK;
+}
+
+// class ids (host or device) -> device copy + per-class sizes; false on an id outside [0, ncls)
+bool stage_classes(Scratch& s, const int32_t* cls, int64_t n, int ncls, uint32_t flags, const int** cls_dev,
+                   std::vector<int>* sizes) {
+  std::vector<int32_t> hbuf;
+  const int32_t* hc = cls;
+  if (flags & EB2_FLAG_DEVICE_INPUT) {
+    hbuf.resize(n);
+    CU(cudaMemcpyAsync(hbuf.data(), cls, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.c.stream));
+    CU(cudaStreamSynchronize(s.c.stream));
+    hc = hbuf.data();
+    *cls_dev = cls;
+  } else {
+    int* dv = s.dev<int>(n);
+    CU(cudaMemcpyAsync(dv, cls, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s.c.stream));
+    *cls_dev = dv;
+  }
+  sizes->assign(ncls, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (hc[i] < 0 || hc[i] >= ncls) return false;
+    (*sizes)[hc[i]]++;
+  }
+  return true;
+}
+
+template <typename F>
+int guarded(int dev, F&& body) {
+  try {
+    Ctx& c = get_ctx(dev);
+    std::lock_guard<std::mutex> g(c.mu);
+    return body(c);
+  } catch (const CudaFail& f) {
+    return fail(EB2_ERR_CUDA, "CUDA error %d (%s) in %s at eb2_lib.cu:%d", (int)f.e, cudaGetErrorString(f.e), f.what, f.line);
+  } catch (const std::bad_alloc&) {
+    return fail(EB2_ERR_CUDA, "host allocation failed");
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* eb2_last_error(void) { return g_err.c_str(); }
+const char* eb2_version(void) { return "ennemi_b200 0.1 (sm_100a)"; }
+
+int eb2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int eb2_init(void) {
+  const int n = eb2_device_count();
+  if (n == 0) return fail(EB2_ERR_CUDA, "no CUDA device available");
+  try {
+    for (int d = 0; d < n && d < kMaxDev; ++d) get_ctx(d);
+  } catch (const CudaFail& f) {
+    return fail(EB2_ERR_CUDA, "CUDA error %d (%s) in %s", (int)f.e, cudaGetErrorString(f.e), f.what);
+  }
+  return EB2_OK;
+}
+
+int eb2_shutdown(void) {
+  std::lock_guard<std::mutex> g(g_init_mu);
+  for (int d = 0; d < kMaxDev; ++d) {
+    Ctx& c = g_ctx[d];
+    if (!c.ready) continue;
+    std::lock_guard<std::mutex> g2(c.mu);
+    cudaSetDevice(c.dev);
+    cudaStreamSynchronize(c.stream);
+    for (auto& e : c.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c.stream);
+    cudaFreeHost(c.pinned);
+    c.pinned = nullptr;
+    c.ready = false;
+  }
+  return EB2_OK;
+}
+
+int eb2_last_timing(int dev, double* ms, int* launches) {
+  if (dev < 0 || dev >= kMaxDev || !g_ctx[dev].ready) return fail(EB2_ERR_ARG, "device %d has no context", dev);
+  if (ms) for (int i = 0; i < 5; ++i) ms[i] = g_ctx[dev].last_ms[i];
+  if (launches) *launches = g_ctx[dev].last_launches;
+  return EB2_OK;
+}
+
+// ---- a1: KSG ------------------------------------------------------------------------------------
+int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t flags, int64_t row_lo, int64_t row_hi,
+                    double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+  if (int rc0 = check_common(coords, n, 2, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, 2, n, flags, ci.nonfinite);
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    PointSet ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1);
+    TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
+    mark(s, 1);
+    double* eps = s.dev<double>(ps.stride);
+    double* radius = s.dev<double>(ps.stride);
+    run_knn(s, ps, rows_range(0, 2), 2, k, self, eps, ci.pairs);
+    mark(s, 2);
+    radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
+    s.launches++;
+    int* nx = s.dev<int>(ps.stride);
+    int* ny = s.dev<int>(ps.stride);
+    if (flags & EB2_FLAG_BRUTE_COUNT) {
+      CountOut out; out.e0 = nx; out.e1 = ny;
+      run_count(s, ps, ps, 0, 2, RowSel{}, RowSel{}, rows_range(0, 2), rows_range(0, 2), radius, self, false, out, ci.pairs);
+    } else {
+      const double* xs = ps.P;                       // row 0 is already ascending when the set is sorted by x
+      if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
+      double* ys = s.dev<double>(n);
+      sort_keys(s, raw + n, ys, (int)n);
+      TileSet all = make_tiles(s, ps, row_lo, row_hi, false, 0, (int)n);
+      run_search(s, ps.P, radius, xs, all, nx);
+      run_search(s, ps.P + ps.stride, radius, ys, all, ny);
+    }
+    mark(s, 3);
+    double* out4 = run_psi(s, PSI_AB, nx, ny, nullptr, nullptr, self);
+    mark(s, 4);
+    const int* cnts[3] = {nx, ny, nullptr};
+    Outputs o; o.eps = eps_out; o.cnt[0] = nx_out; o.cnt[1] = ny_out;
+    export_outputs(s, ps, eps, cnts, o);
+    return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+  });
+}
+
+int eb2_ksg_mi_finish(const double* partial, int64_t n, int k, double* value) {
+  if (!partial || !value || n <= 0 || k <= 0) return fail(EB2_ERR_ARG, "bad argument");
+  *value = psi_host((double)n) + psi_host((double)k) - psi_mean(partial, n);    // :113
+  return EB2_OK;
+}
+
+int eb2_ksg_mi(int dev, const double* coords, int64_t n, int k, uint32_t flags, double* value, double* eps_out,
+               int64_t* nx_out, int64_t* ny_out) {
+  if (!value) return fail(EB2_ERR_ARG, "value is NULL");
+  double partial[EB2_P_LEN];
+  const int rc = eb2_ksg_mi_rows(dev, coords, n, k, flags, 0, n, partial, eps_out, nx_out, ny_out);
+  if (rc) return rc;
+  return eb2_ksg_mi_finish(partial, n, k, value);
+}
+
+// ---- a2: Frenzel-Pompe ----------------------------------------------------------------------------
+int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uint32_t flags, int64_t row_lo,
+                 int64_t row_hi, double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+  const int d = 2 + c_dim;
+  if (int rc0 = check_common(coords, n, d, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, d, n, flags, ci.nonfinite);
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    // every space on this path (xyz, xz, yz, z) contains z_0: sort by it
+    PointSet ps = build_point_set(s, raw, d, n, nullptr, {}, prune ? 2 : -1);
+    TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
+    mark(s, 1);
+    double* eps = s.dev<double>(ps.stride);
+    double* radius = s.dev<double>(ps.stride);
+    run_knn(s, ps, rows_range(0, d), d, k, self, eps, ci.pairs);
+    mark(s, 2);
+    radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
+    s.launches++;
+    int* nz = s.dev<int>(ps.stride);
+    int* nxz = s.dev<int>(ps.stride);
+    int* nyz = s.dev<int>(ps.stride);
+    CountOut out; out.s = nz; out.e0 = nxz; out.e1 = nyz;
+    run_count(s, ps, ps, c_dim, 2, rows_range(2, c_dim), rows_range(2, c_dim), rows_range(0, 2), rows_range(0, 2),
+              radius, self, prune, out, ci.pairs);
+    mark(s, 3);
+    double* out4 = run_psi(s, PSI_AB_MINUS_C, nxz, nyz, nz, nullptr, self);
+    mark(s, 4);
+    const int* cnts[3] = {nxz, nyz, nz};
+    Outputs o; o.eps = eps_out; o.cnt[0] = nxz_out; o.cnt[1] = nyz_out; o.cnt[2] = nz_out;
+    export_outputs(s, ps, eps, cnts, o);
+    return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+  });
+}
+
+int eb2_cmi_finish(const double* partial, int64_t n, int k, double* value) {
+  if (!partial || !value || n <= 0 || k <= 0) return fail(EB2_ERR_ARG, "bad argument");
+  *value = psi_host((double)k) - psi_mean(partial, n);    // :156
+  return EB2_OK;
+}
+
+int eb2_cmi(int dev, const double* coords, int64_t n, int c_dim, int k, uint32_t flags, double* value, double* eps_out,
+            int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  if (!value) return fail(EB2_ERR_ARG, "value is NULL");
+  double partial[EB2_P_LEN];
+  const int rc = eb2_cmi_rows(dev, coords, n, c_dim, k, flags, 0, n, partial, eps_out, nxz_out, nyz_out, nz_out);
+  if (rc) return rc;
+  return eb2_cmi_finish(partial, n, k, value);
+}
+
+// ---- a3: Ross -------------------------------------------------------------------------------------
+int eb2_ross_mi(int dev, const double* coords, const int32_t* cls, int64_t n, int ncls, int k, uint32_t flags,
+                double* value, double* eps_out, int64_t* nfull_out) {
+  if (int rc0 = check_common(coords, n, 1, k)) return rc0;
+  if (!cls || ncls < 1 || !value) return fail(EB2_ERR_ARG, "cls/ncls/value invalid");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, 1, n, flags, ci.nonfinite);
+    const int* cls_dev = nullptr;
+    std::vector<int> sizes;
+    if (!stage_classes(s, cls, n, ncls, flags, &cls_dev, &sizes)) return fail(EB2_ERR_ARG, "class id outside [0, ncls)");
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    PointSet ps = build_point_set(s, raw, 1, n, cls_dev, sizes, prune ? 0 : -1);
+    TileSet self = make_tiles(s, ps, 0, n, true, 0, 0);
+    mark(s, 1);
+    double* eps = s.dev<double>(ps.stride);
+    double* radius = s.dev<double>(ps.stride);
+    run_knn(s, ps, rows_range(0, 1), 1, k, self, eps, ci.pairs);      // :194 within the class
+    mark(s, 2);
+    radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
+    s.launches++;
+    int* nfull = s.dev<int>(ps.stride);
+    if (flags & EB2_FLAG_BRUTE_COUNT) {
+      TileSet all = make_tiles(s, ps, 0, n, false, 0, (int)ps.stride);
+      CountOut out; out.e0 = nfull;
+      run_count(s, ps, ps, 0, 1, RowSel{}, RowSel{}, rows_range(0, 1), rows_range(0, 1), radius, all, false, out, ci.pairs);
+    } else {
+      double* xs = s.dev<double>(n);
+      sort_keys(s, raw, xs, (int)n);
+      TileSet all = make_tiles(s, ps, 0, n, false, 0, (int)n);
+      run_search(s, ps.P, radius, xs, all, nfull);                     // :196 over all x
+    }
+    mark(s, 3);
+    double* out4 = run_psi(s, PSI_A, nfull, nullptr, nullptr, nullptr, self);
+    mark(s, 4);
+    const int* cnts[3] = {nfull, nullptr, nullptr};
+    Outputs o; o.eps = eps_out; o.cnt[0] = nfull_out;
+    export_outputs(s, ps, eps, cnts, o);
+    double partial[EB2_P_LEN];
+    const int rc = finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+    if (rc) return rc;
+    double weighted = 0.0;                                             // :199
+    for (int g = 0; g < ncls; ++g)
+      if (sizes[g] > 0) weighted += psi_host((double)sizes[g]) * ((double)sizes[g] / (double)n);
+    *value = psi_host((double)n) + psi_host((double)k) - psi_mean(partial, n) - weighted;   // :200
+    return EB2_OK;
+  });
+}
+
+// ---- a4: conditional Ross ---------------------------------------------------------------------------
+int eb2_ross_cmi(int dev, const double* coords, const int32_t* cls, int64_t n, int c_dim, int ncls, int k,
+                 uint32_t flags, double* value, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+  const int d = 1 + c_dim;
+  if (int rc0 = check_common(coords, n, d, k)) return rc0;
+  if (!cls || ncls < 1 || !value) return fail(EB2_ERR_ARG, "cls/ncls/value invalid");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, d, n, flags, ci.nonfinite);
+    const int* cls_dev = nullptr;
+    std::vector<int> sizes;
+    if (!stage_classes(s, cls, n, ncls, flags, &cls_dev, &sizes)) return fail(EB2_ERR_ARG, "class id outside [0, ncls)");
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    // A: grouped by class (and ascending in z_0 inside a class); B: every row, ascending in z_0
+    PointSet A = build_point_set(s, raw, d, n, cls_dev, sizes, prune ? 1 : -1);
+    PointSet B = A;
+    if (prune) B = build_point_set(s, raw, d, n, nullptr, {}, 1);
+    TileSet self = make_tiles(s, A, 0, n, true, 0, 0);
+    TileSet all = make_tiles(s, A, 0, n, false, 0, prune ? (int)n : (int)A.stride);
+    mark(s, 1);
+    double* eps = s.dev<double>(A.stride);
+    double* radius = s.dev<double>(A.stride);
+    run_knn(s, A, rows_range(0, d), d, k, self, eps, ci.pairs);        // :240 (x,z) within the class
+    mark(s, 2);
+    radius_kernel<<<cdiv(A.stride, 256), 256, 0, c.stream>>>(eps, radius, A.stride);
+    s.launches++;
+    int* nz = s.dev<int>(A.stride);
+    int* nxz = s.dev<int>(A.stride);
+    int* nyz = s.dev<int>(A.stride);
+    CountOut o_all; o_all.s = nz; o_all.e0 = nxz;                      // :243, :245 over all rows
+    run_count(s, A, B, c_dim, 1, rows_range(1, c_dim), rows_range(1, c_dim), rows_range(0, 1), rows_range(0, 1),
+              radius, all, prune, o_all, ci.pairs);
+    CountOut o_cls; o_cls.s = nyz;                                     // :244 z within the class
+    run_count(s, A, A, c_dim, 0, rows_range(1, c_dim), rows_range(1, c_dim), RowSel{}, RowSel{}, radius, self, prune,
+              o_cls, ci.pairs);
+    mark(s, 3);
+    double* out4 = run_psi(s, PSI_AB_MINUS_C, nxz, nyz, nz, nullptr, self);
+    mark(s, 4);
+    const int* cnts[3] = {nxz, nyz, nz};
+    Outputs o; o.eps = eps_out; o.cnt[0] = nxz_out; o.cnt[1] = nyz_out; o.cnt[2] = nz_out;
+    export_outputs(s, A, eps, cnts, o);
+    double partial[EB2_P_LEN];
+    const int rc = finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+    if (rc) return rc;
+    *value = psi_host((double)k) - psi_mean(partial, n);               // :247
+    return EB2_OK;
+  });
+}
+
+// ---- a5: k-NN entropy ---------------------------------------------------------------------------------
+int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, int64_t row_lo,
+                     int64_t row_hi, double* partial, double* dist_out) {
+  if (int rc0 = check_common(coords, n, m, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, m, n, flags, ci.nonfinite);
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    PointSet ps = build_point_set(s, raw, m, n, nullptr, {}, prune ? 0 : -1);
+    TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
+    mark(s, 1);
+    double* dist = s.dev<double>(ps.stride);
+    run_knn(s, ps, rows_range(0, m), m, k, self, dist, ci.pairs);      // :39
+    mark(s, 2);
+    mark(s, 3);
+    double* out4 = run_psi(s, LOG_DIST, nullptr, nullptr, nullptr, dist, self);
+    mark(s, 4);
+    const int* cnts[3] = {nullptr, nullptr, nullptr};
+    Outputs o; o.eps = dist_out;
+    export_outputs(s, ps, dist, cnts, o);
+    return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+  });
+}
+
+int eb2_entropy_finish(const double* partial, int64_t n, int m, int k, double* value) {
+  if (!partial || !value || n <= 0 || k <= 0 || m <= 0) return fail(EB2_ERR_ARG, "bad argument");
+  const double mean_log = partial[EB2_P_SUM] / (double)n;
+  *value = psi_host((double)n) - psi_host((double)k) + m * (mean_log + std::log(2.0));   // :42
+  return EB2_OK;
+}
+
+int eb2_entropy(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, double* value, double* dist_out) {
+  if (!value) return fail(EB2_ERR_ARG, "value is NULL");
+  double partial[EB2_P_LEN];
+  const int rc = eb2_entropy_rows(dev, coords, n, m, k, flags, 0, n, partial, dist_out);
+  if (rc) return rc;
+  return eb2_entropy_finish(partial, n, m, k, value);
+}
+
+// ---- a6: digamma on the device ---------------------------------------------------------------------------
+int eb2_psi(int dev, const int64_t* counts, int64_t n, double* out) {
+  if (!counts || !out || n <= 0) return fail(EB2_ERR_ARG, "bad argument");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    long long* dc = s.dev<long long>(n);
+    double* dout = s.dev<double>(n);
+    CU(cudaMemcpyAsync(dc, counts, sizeof(long long) * n, cudaMemcpyHostToDevice, c.stream));
+    psi_array_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(dc, n, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    c.last_launches = 1;
+    return EB2_OK;
+  });
+}
+
+// ---- primitives ---------------------------------------------------------------------------------------------
+int eb2_kth_distance(int dev, const double* coords, const int32_t* cls, int64_t n, int d, int ncls, int k,
+                     uint32_t flags, double* out) {
+  if (int rc0 = check_common(coords, n, d, k)) return rc0;
+  if (!out) return fail(EB2_ERR_ARG, "out is NULL");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    const double* raw = stage_coords(s, coords, d, n, flags, ci.nonfinite);
+    const int* cls_dev = nullptr;
+    std::vector<int> sizes;
+    if (cls && !stage_classes(s, cls, n, ncls, flags, &cls_dev, &sizes)) return fail(EB2_ERR_ARG, "class id outside [0, ncls)");
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    PointSet ps = build_point_set(s, raw, d, n, cls_dev, sizes, prune ? 0 : -1);
+    TileSet self = make_tiles(s, ps, 0, n, true, 0, 0);
+    mark(s, 1);
+    double* eps = s.dev<double>(ps.stride);
+    run_knn(s, ps, rows_range(0, d), d, k, self, eps, ci.pairs);
+    mark(s, 2); mark(s, 3); mark(s, 4);
+    const int* cnts[3] = {nullptr, nullptr, nullptr};
+    Outputs o; o.eps = out;
+    export_outputs(s, ps, eps, cnts, o);
+    double* out4 = s.dev<double>(4);
+    CU(cudaMemsetAsync(out4, 0, sizeof(double) * 4, c.stream));
+    return finish_call(s, out4, ci.pairs, ci.nonfinite, n, nullptr);
+  });
+}
+
+int eb2_ball_count(int dev, const double* coords, const int32_t* cls, int64_t n, int d, int ncls, int within_class,
+                   const double* radius, uint32_t flags, int64_t* out) {
+  if (int rc0 = check_common(coords, n, d, 1)) return rc0;
+  if (!out || !radius) return fail(EB2_ERR_ARG, "out/radius is NULL");
+  if (flags & EB2_FLAG_DEVICE_INPUT) return fail(EB2_ERR_ARG, "eb2_ball_count takes host buffers only");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CallInit ci = begin_call(s);
+    // the radius travels as one more row so that it is permuted with the points
+    double* raw = s.dev<double>(static_cast<size_t>(d + 1) * n);
+    CU(cudaMemcpyAsync(raw, coords, sizeof(double) * d * n, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(raw + static_cast<int64_t>(d) * n, radius, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream));
+    nonfinite_kernel<<<cdiv(static_cast<int64_t>(d) * n, 256), 256, 0, c.stream>>>(raw, static_cast<int64_t>(d) * n, ci.nonfinite);
+    s.launches++;
+    const int* cls_dev = nullptr;
+    std::vector<int> sizes;
+    const bool seg = cls && within_class;
+    if (seg && !stage_classes(s, cls, n, ncls, flags, &cls_dev, &sizes)) return fail(EB2_ERR_ARG, "class id outside [0, ncls)");
+    const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    PointSet ps = build_point_set(s, raw, d + 1, n, seg ? cls_dev : nullptr, sizes, prune ? 0 : -1);
+    TileSet self = make_tiles(s, ps, 0, n, true, 0, 0);
+    mark(s, 1); mark(s, 2);
+    int* cnt = s.dev<int>(ps.stride);
+    const double* rad = ps.P + static_cast<int64_t>(d) * ps.stride;
+    if (d == 1 && !(flags & EB2_FLAG_BRUTE_COUNT) && prune) {
+      // segment slices of row 0 are ascending: exact binary search
+      TileSet sl = make_tiles(s, ps, 0, n, true, 0, 0);
+      // search_kernel indexes `sorted + c_lo` with c_len valid entries, which is exactly the segment
+      run_search(s, ps.P, rad, ps.P, sl, cnt);
+    } else {
+      CountOut co; co.s = cnt;
+      run_count(s, ps, ps, d, 0, rows_range(0, d), rows_range(0, d), RowSel{}, RowSel{}, rad, self, prune, co, ci.pairs);
+    }
+    mark(s, 3); mark(s, 4);
+    const int* cnts[3] = {cnt, nullptr, nullptr};
+    Outputs o; o.cnt[0] = out;
+    export_outputs(s, ps, nullptr, cnts, o);
+    double* out4 = s.dev<double>(4);
+    CU(cudaMemsetAsync(out4, 0, sizeof(double) * 4, c.stream));
+    return finish_call(s, out4, ci.pairs, ci.nonfinite, n, nullptr);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+"""Multi-GPU operation with one process per GPU (``torchrun`` / ``torch.distributed``).
+
+Two partitions of the work, matching the two ways the path shards:
+
+* **row sharding of one large estimate** — every rank holds the full point set, estimates the query
+  rows of its own shard and contributes an 8-double block of raw sums; one ``all_reduce(SUM)``
+  (NCCL over NVLink on GPUs, gloo in CPU tests) combines them and every rank finishes the same
+  value.  This is the only collective on the data path.
+* **task fan-out** — independent (variable pair / lag) tasks are dealt round-robin to the ranks, each
+  rank runs its share on its own GPU, and one ``all_gather`` of the scalar results rebuilds the
+  task-ordered list on every rank.  No data-path collective.
+
+``torch`` is imported lazily: the single-process API does not need it.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _devices, _native
+
+_enabled = False
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def is_initialized() -> bool:
+    try:
+        dist = _dist()
+    except Exception:
+        return False
+    return dist.is_available() and dist.is_initialized()
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) outside ``torch.distributed``."""
+    if not is_initialized():
+        return 0, 1
+    dist = _dist()
+    return dist.get_rank(), dist.get_world_size()
+
+
+def enable_task_fanout(on: bool = True) -> None:
+    """Make ``estimate_mi`` / ``pairwise_mi`` deal their tasks across the ranks of the default
+    process group (every rank must then make the same call with the same data)."""
+    global _enabled
+    _enabled = on
+
+
+def task_fanout_enabled() -> bool:
+    return _enabled and is_initialized() and world()[1] > 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous row range of ``rank``; the ranges of all ranks tile [0, n) exactly."""
+    return (n * rank) // world_size, (n * (rank + 1)) // world_size
+
+
+def _all_reduce_sum(block: np.ndarray, group=None) -> np.ndarray:
+    """Sum of an fp64 block over the ranks.  With the NCCL backend the block is reduced on the
+    rank's GPU (over NVLink/NVSwitch); with gloo on the host."""
+    if not is_initialized() or world()[1] == 1:
+        return block
+    import torch
+    dist = _dist()
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(np.ascontiguousarray(block, dtype=np.float64))
+    if backend == "nccl":
+        dev = torch.device("cuda", _devices.current())
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy()
+
+
+def _coords_ptr(coords) -> Tuple[int, int]:
+    """(address, extra flags) of a (d, n) block given as a numpy array or a CUDA torch tensor."""
+    if isinstance(coords, np.ndarray):
+        return coords.ctypes.data, 0
+    return int(coords.data_ptr()), _native.FLAG_DEVICE_INPUT      # torch tensor resident on this rank's GPU
+
+
+def sharded_ksg_mi(coords, k: int = 3, flags: int = 0, group=None) -> float:
+    """KSG MI of ``coords = [x; y]`` (2 x n, replicated on every rank) with query rows sharded
+    over the ranks; one sum-allreduce of the partial block.  ``coords`` may be a contiguous numpy
+    array (host) or a CUDA ``torch`` tensor on the rank's device."""
+    rank, size = world()
+    n = int(coords.shape[1])
+    lo, hi = shard_bounds(n, rank, size)
+    ptr, extra = _coords_ptr(coords)
+    part = _native.ksg_mi_rows(ptr, n, k, lo, hi, dev=_devices.current(), flags=flags | extra)
+    return _native.ksg_mi_finish(_all_reduce_sum(part, group), n, k)
+
+
+def sharded_cmi(coords, k: int = 3, flags: int = 0, group=None) -> float:
+    """Frenzel-Pompe CMI of ``coords = [x; y; z...]`` with query rows sharded over the ranks."""
+    rank, size = world()
+    d, n = int(coords.shape[0]), int(coords.shape[1])
+    lo, hi = shard_bounds(n, rank, size)
+    ptr, extra = _coords_ptr(coords)
+    part = _native.cmi_rows(ptr, n, d - 2, k, lo, hi, dev=_devices.current(), flags=flags | extra)
+    return _native.cmi_finish(_all_reduce_sum(part, group), n, k)
+
+
+def sharded_entropy(coords, k: int = 3, flags: int = 0, group=None) -> float:
+    """k-NN entropy of ``coords`` (m x n) with query rows sharded over the ranks."""
+    rank, size = world()
+    m, n = int(coords.shape[0]), int(coords.shape[1])
+    lo, hi = shard_bounds(n, rank, size)
+    ptr, extra = _coords_ptr(coords)
+    part = _native.entropy_rows(ptr, n, m, k, lo, hi, dev=_devices.current(), flags=flags | extra)
+    return _native.entropy_finish(_all_reduce_sum(part, group), n, m, k)
+
+
+def fan_out(func: Callable, params: Sequence, callback: Optional[Callable[[int], None]] = None,
+            group=None) -> List[float]:
+    """Runs ``func(params[i])`` for the tasks ``i = rank, rank + world, ...`` on this rank and returns
+    the full task-ordered result list on every rank (one all_gather of fp64 scalars)."""
+    rank, size = world()
+    mine = list(range(rank, len(params), size))
+    local = np.full(len(range(0, len(params), size)) if size else 0, np.nan)
+    for slot, i in enumerate(mine):
+        local[slot] = func(params[i])
+        if callback is not None:
+            callback(i)
+    if size == 1:
+        return [float(v) for v in local[:len(params)]]
+    import torch
+    dist = _dist()
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(local)
+    if backend == "nccl":
+        t = t.to(torch.device("cuda", _devices.current()))
+    gathered = [torch.empty_like(t) for _ in range(size)]
+    dist.all_gather(gathered, t, group=group)
+    table = np.stack([g.cpu().numpy() for g in gathered])          # [rank][slot]
+    return [float(table[i % size, i // size]) for i in range(len(params))]

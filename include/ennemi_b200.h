@@ -1,0 +1,134 @@
+/* ennemi_b200 — C ABI of the B200 (sm_100a) k-NN mutual-information library.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (polsys/ennemi 1.5.0)
+ * has no FFI of its own: the seam is the five private Python estimators imported at
+ * ennemi/_driver.py:18-21 and called at _driver.py:222-226 and :815-832.  Each eb2_* estimator
+ * below replaces one of them; the arithmetic it replaces is the scipy.spatial.cKDTree calls at
+ * ennemi/_entropy_estimators.py:39,108-110,142,152-154,194-196,240-245 and _psi at :327-350.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array is contiguous fp64 / int32 / int64.
+ *  - `coords` is DIMENSION-MAJOR: d blocks of n doubles, block t = coordinate t of every
+ *    observation (the host transposes the reference's (n, d) row-major arrays once).
+ *  - buffers are HOST pointers owned by the caller for the duration of the call, unless
+ *    EB2_FLAG_DEVICE_INPUT is set in `flags`, in which case `coords`/`cls` are device pointers on
+ *    device `dev` (used to measure the kernels with inputs already resident in HBM).
+ *  - optional outputs (eps_out, count outputs) may be NULL; when given they are host arrays of
+ *    length n in the caller's original row order.
+ *  - `partial` is an 8-double block of raw sums for the rows [row_lo, row_hi) (see EB2_P_*),
+ *    so that query rows can be sharded over GPUs/ranks and combined with one sum-allreduce;
+ *    eb2_*_finish turns the (summed) block into the estimate.
+ *  - return value: 0 on success, an EB2_ERR_* code otherwise; eb2_last_error() gives the
+ *    thread-local message.  There is no CPU fallback: without a usable CUDA device every
+ *    estimator returns EB2_ERR_CUDA.
+ *  - thread safety: all entry points may be called concurrently; calls on the same `dev`
+ *    serialise on that device's stream and workspace.
+ */
+#ifndef ENNEMI_B200_H
+#define ENNEMI_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define EB2_API __attribute__((visibility("default")))
+#else
+#define EB2_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB2_OK 0
+#define EB2_ERR_CUDA 1        /* CUDA runtime error / no device */
+#define EB2_ERR_ARG 2         /* bad argument (n, k, d, pointers) */
+#define EB2_ERR_NONFINITE 3   /* non-finite coordinate: mirrors cKDTree's ValueError */
+#define EB2_ERR_UNSUPPORTED 4 /* dimension above EB2_MAX_DIM */
+
+#define EB2_MAX_DIM 12
+
+/* flags */
+#define EB2_FLAG_DEVICE_INPUT 1u /* coords / cls are device pointers on `dev` */
+#define EB2_FLAG_BRUTE_COUNT 2u  /* count 1-D marginals with the tiled all-pairs kernel instead of sort+search */
+#define EB2_FLAG_NO_PRUNE 4u     /* visit every candidate tile (pure brute force); default is exact sorted-window pruning */
+
+/* layout of the 8-double partial block */
+#define EB2_P_SUM 0   /* sum over rows of the per-row term (psi combination, or log(dist)) */
+#define EB2_P_ZERO_A 1 /* number of rows whose first  count is 0 (psi(0) = inf in the reference) */
+#define EB2_P_ZERO_B 2 /* ... second count */
+#define EB2_P_ZERO_C 3 /* ... third count */
+#define EB2_P_ROWS 4  /* rows reduced */
+#define EB2_P_PAIRS 5 /* point pairs evaluated by the all-pairs kernels (work counter for the roofline) */
+#define EB2_P_LEN 8
+
+EB2_API int eb2_init(void);            /* optional; creates the per-device contexts eagerly */
+EB2_API int eb2_shutdown(void);        /* frees every device workspace */
+EB2_API int eb2_device_count(void);    /* usable CUDA devices (0 when there is none) */
+EB2_API const char* eb2_last_error(void);
+EB2_API const char* eb2_version(void);
+
+/* a1  _estimate_single_mi(x, y, k)            _entropy_estimators.py:69-113
+ * coords = [x ; y] (2 x n).  value = psi(n) + psi(k) - mean(psi(nx) + psi(ny)). */
+EB2_API int eb2_ksg_mi(int dev, const double* coords, int64_t n, int k, uint32_t flags,
+               double* value, double* eps_out, int64_t* nx_out, int64_t* ny_out);
+EB2_API int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t flags,
+                    int64_t row_lo, int64_t row_hi, double* partial,
+                    double* eps_out, int64_t* nx_out, int64_t* ny_out);
+EB2_API int eb2_ksg_mi_finish(const double* partial, int64_t n, int k, double* value);
+
+/* a2  _estimate_conditional_mi(x, y, cond, k)  _entropy_estimators.py:116-156
+ * coords = [x ; y ; z_0 .. z_{c-1}] ((2+c) x n).
+ * value = psi(k) - mean(psi(nxz) + psi(nyz) - psi(nz)). */
+EB2_API int eb2_cmi(int dev, const double* coords, int64_t n, int c, int k, uint32_t flags,
+            double* value, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out);
+EB2_API int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c, int k, uint32_t flags,
+                 int64_t row_lo, int64_t row_hi, double* partial,
+                 double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out);
+EB2_API int eb2_cmi_finish(const double* partial, int64_t n, int k, double* value);
+
+/* a3  _estimate_semidiscrete_mi(x, y, k)       _entropy_estimators.py:159-200
+ * coords = [x] (1 x n); cls[i] in [0, ncls) = index of y_i in np.unique(y).
+ * value = psi(n) + psi(k) - mean(psi(n_full)) - sum_c psi(n_c) n_c / n. */
+EB2_API int eb2_ross_mi(int dev, const double* coords, const int32_t* cls, int64_t n, int ncls, int k, uint32_t flags,
+                double* value, double* eps_out, int64_t* nfull_out);
+
+/* a4  _estimate_conditional_semidiscrete_mi(x, y, cond, k)   _entropy_estimators.py:203-247
+ * coords = [x ; z_0 .. z_{c-1}] ((1+c) x n); cls as above.
+ * value = psi(k) - mean(psi(nxz) + psi(nyz) - psi(nz)). */
+EB2_API int eb2_ross_cmi(int dev, const double* coords, const int32_t* cls, int64_t n, int c, int ncls, int k,
+                 uint32_t flags, double* value, double* eps_out,
+                 int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out);
+
+/* a5  _estimate_single_entropy(x, k)           _entropy_estimators.py:21-42
+ * coords = [x_0 .. x_{m-1}] (m x n).
+ * value = psi(n) - psi(k) + m (mean(log dist) + log 2). */
+EB2_API int eb2_entropy(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags,
+                double* value, double* dist_out);
+EB2_API int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags,
+                     int64_t row_lo, int64_t row_hi, double* partial, double* dist_out);
+EB2_API int eb2_entropy_finish(const double* partial, int64_t n, int m, int k, double* value);
+
+/* a6  _psi(x)                                  _entropy_estimators.py:327-350
+ * digamma of non-negative integers evaluated ON THE DEVICE with the reference's expansion;
+ * out[i] = +inf where counts[i] == 0. */
+EB2_API int eb2_psi(int dev, const int64_t* counts, int64_t n, double* out);
+
+/* the two primitives on their own (parity tests, building blocks):
+ * kth:   out[i] = (k+1)-th smallest Chebyshev distance from row i to all rows (self included);
+ *        with cls != NULL only rows of the same class are candidates.
+ * count: out[i] = #{j : max_t |a_it - a_jt| <= radius_i}; with cls != NULL and within_class != 0
+ *        only rows of the same class are candidates. */
+EB2_API int eb2_kth_distance(int dev, const double* coords, const int32_t* cls, int64_t n, int d, int ncls, int k,
+                     uint32_t flags, double* out);
+EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, int64_t n, int d, int ncls,
+                   int within_class, const double* radius, uint32_t flags, int64_t* out);
+
+/* timing of the last estimator call on `dev`, from CUDA events on the library's stream:
+ * ms[0] total device span (first H2D to last D2H), ms[1] k-NN kernel, ms[2] marginal counting,
+ * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
+EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENNEMI_B200_H */

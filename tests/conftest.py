@@ -1,0 +1,102 @@
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def has_gpu() -> bool:
+    try:
+        from ennemi_b200 import _native
+        return _native.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU must fail loudly, not skip: nothing to do here.  Without `-m`,
+    # GPU tests are skipped when no device is present so that a plain `pytest tests` works anywhere.
+    if config.getoption("-m"):
+        return
+    if has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class OracleBackend:
+    """Stands in for ``ennemi_b200._native`` in CPU tests of the HOST logic: same function
+    signatures, answers computed by the CPU oracle.  Never used by the product."""
+
+    def __init__(self, backend="scipy"):
+        import oracle
+        self.o = oracle
+        self.backend = backend
+
+    @staticmethod
+    def _rows(coords):
+        return [np.ascontiguousarray(r) for r in coords]
+
+    def ksg_mi(self, coords, k, dev=0, flags=0, details=False):
+        r = self.o.ksg_mi(coords[0], coords[1], k, backend=self.backend)
+        return (r["value"], r) if details else r["value"]
+
+    def cmi(self, coords, k, dev=0, flags=0, details=False):
+        r = self.o.conditional_mi(coords[0], coords[1], coords[2:].T, k, backend=self.backend)
+        return (r["value"], r) if details else r["value"]
+
+    def ross_mi(self, coords, cls, ncls, k, dev=0, flags=0, details=False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = self.o.semidiscrete_mi(coords[0], cls, k, backend=self.backend)
+        return (r["value"], r) if details else r["value"]
+
+    def ross_cmi(self, coords, cls, ncls, k, dev=0, flags=0, details=False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = self.o.conditional_semidiscrete_mi(coords[0], cls, coords[1:].T, k, backend=self.backend)
+        return (r["value"], r) if details else r["value"]
+
+    def entropy(self, coords, k, dev=0, flags=0, details=False):
+        r = self.o.knn_entropy(coords.T, k, backend=self.backend)
+        return (r["value"], r) if details else r["value"]
+
+    def psi(self, counts, dev=0):
+        return np.asarray(self.o.psi(np.asarray(counts)), dtype=np.float64)
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """Routes the estimator seam to the CPU oracle so that host logic can be tested without a GPU."""
+    from ennemi_b200 import _native, _devices
+    fake = OracleBackend()
+    for name in ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi"):
+        monkeypatch.setattr(_native, name, getattr(fake, name))
+    monkeypatch.setattr(_native, "device_count", lambda: 1)
+    monkeypatch.setattr(_devices, "visible", lambda: [0])
+    return fake
+
+
+@pytest.fixture(scope="session")
+def golden_estimators():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "estimators.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    return {n: {k.split("/")[1]: g[k] for k in g.files if k.startswith(n + "/")} for n in names}
+
+
+@pytest.fixture(scope="session")
+def golden_api():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "api.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    return {n: {k.split("/")[1]: g[k] for k in g.files if k.startswith(n + "/")} for n in names}

@@ -1,0 +1,184 @@
+"""Host logic (lag alignment, masks, NaN dropping, rescaling, dispatch, pandas wrapping, scheduling)
+against the outputs of the reference's public API stored in ``tests/golden/api.npz``.
+
+The estimator seam is routed to the CPU oracle (fixture ``oracle_backend``), whose values are
+bit-identical to the reference's, so every comparison here is exact equality."""
+import threading
+import warnings
+
+import numpy as np
+import pytest
+
+import ennemi_b200 as eb
+
+
+def eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def test_estimate_mi_cases(oracle_backend, golden_api):
+    g = golden_api
+    x3, y, cond, mask, lags = (g["inputs"][k] for k in ("x3", "y", "cond", "mask", "lags"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert eq(eb.estimate_mi(y, x3, lags), g["mi_lags"]["out"])
+        assert eq(eb.estimate_mi(y, x3, lags, k=5, preprocess=False), g["mi_lags_k5_nopre"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond), g["mi_cond"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=1), g["mi_cond_lag1"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=g["mi_cond_lag2d"]["cond_lag"]),
+                  g["mi_cond_lag2d"]["out"])
+        assert eq(eb.estimate_mi(y, x3, lags, mask=mask), g["mi_mask"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, 0], [0, 2], mask=mask, cond=cond[:, 0]), g["mi_mask_cond"]["out"])
+        assert eq(eb.estimate_corr(y, x3, lags), g["corr_lags"]["out"])
+        assert eq(eb.estimate_mi(g["mi_dropnan"]["ynan"], g["mi_dropnan"]["xnan"], [0, 1], drop_nan=True),
+                  g["mi_dropnan"]["out"])
+        yd, xd = g["mi_discrete_y"]["yd"], g["mi_discrete_x"]["xd"]
+        assert eq(eb.estimate_mi(yd, x3, [0, 2], discrete_y=True), g["mi_discrete_y"]["out"])
+        assert eq(eb.estimate_mi(y, xd, [0, 2], discrete_x=True, k=4), g["mi_discrete_x"]["out"])
+        assert eq(eb.estimate_mi(yd, x3[:, :2], [0, 1], discrete_y=True, cond=cond), g["mi_discrete_y_cond"]["out"])
+        assert eq(eb.estimate_mi(y, xd, [0, 1], discrete_x=True, cond=cond[:, 0]), g["mi_discrete_x_cond"]["out"])
+        assert eq(eb.estimate_mi(yd, xd, [0, 1], discrete_x=True, discrete_y=True), g["mi_discrete_both"]["out"])
+        assert eq(eb.estimate_mi(yd, xd, 0, discrete_x=True, discrete_y=True, cond=(cond[:, 0] > 0).astype(int)),
+                  g["mi_discrete_both_cond"]["out"])
+
+
+def test_pairwise_and_entropy_cases(oracle_backend, golden_api):
+    g = golden_api
+    x3, y, cond, mask = (g["inputs"][k] for k in ("x3", "y", "cond", "mask"))
+    yd, xd = g["mi_discrete_y"]["yd"], g["mi_discrete_x"]["xd"]
+    ynan, xnan = g["mi_dropnan"]["ynan"], g["mi_dropnan"]["xnan"]
+    data5 = np.column_stack((x3, y, cond[:, 0]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert eq(eb.pairwise_mi(x3), g["pairwise"]["out"])
+        assert eq(eb.pairwise_mi(data5, k=4), g["pairwise5"]["out"])
+        assert eq(eb.pairwise_corr(data5), g["pairwise5_corr"]["out"])
+        assert eq(eb.pairwise_mi(np.column_stack((x3, y)), cond=cond, mask=mask), g["pairwise_cond_mask"]["out"])
+        assert eq(eb.pairwise_mi(np.column_stack((x3[:, 0], xd, yd, y)), discrete=[False, True, True, False]),
+                  g["pairwise_discrete"]["out"])
+        assert eq(eb.pairwise_mi(np.column_stack((xnan, ynan)), drop_nan=True), g["pairwise_dropnan"]["out"])
+        assert eq(eb.estimate_entropy(x3), g["ent_cols"]["out"])
+        assert eq(eb.estimate_entropy(x3, multidim=True, k=5), g["ent_multidim"]["out"])
+        assert eq(eb.estimate_entropy(x3[:, :2], cond=cond), g["ent_cond"]["out"])
+        assert eq(eb.estimate_entropy(x3[:, :2], cond=cond[:, 0], multidim=True, mask=mask), g["ent_cond_multidim_mask"]["out"])
+        assert eq(eb.estimate_entropy(ynan, drop_nan=True), g["ent_1d_dropnan"]["out"])
+        assert eq(eb.estimate_entropy(np.column_stack((xd, yd)), discrete=True), g["ent_discrete"]["out"])
+    assert eq(eb.normalize_mi(g["normalize"]["mi"]), g["normalize"]["out"])
+
+
+def test_docs_known_answers(oracle_backend, golden_api):
+    """The 8-digit outputs printed in the reference's docs (tutorial.md:165, :208-210;
+    potential-issues.md:68, :117, :168), regenerated from their snippets."""
+    g = golden_api
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0, 0], [[1, 0.8], [0.8, 1]], size=800)
+    z = rng.normal(0, 1, size=800)
+    out = eb.estimate_corr(data[:, 1], np.column_stack((data[:, 0], z)))
+    assert eq(out, g["doc_tutorial_165"]["out"]) and np.allclose(out, g["doc_tutorial_165"]["printed"], atol=5e-9)
+    rng = np.random.default_rng(1234)
+    x = rng.gamma(1.0, 1.0, size=400); y = np.zeros(400); y[1:] = x[0:-1]; y += rng.normal(0, 0.01, size=400)
+    out = eb.estimate_corr(y, x, lag=[1, 0, -1])
+    assert eq(out, g["doc_tutorial_208"]["out"]) and np.allclose(out, g["doc_tutorial_208"]["printed"], atol=5e-9)
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0.5, 0.5], [[1, 0.8], [0.8, 1]], size=800)
+    out = eb.estimate_mi(np.maximum(0, data[:, 1]), np.maximum(0, data[:, 0]), preprocess=False)
+    assert out.shape == (1, 1) and out[0, 0] == -np.inf
+
+
+def test_error_messages_and_types(oracle_backend):
+    x = np.arange(50.0)
+    y = x ** 2
+    cases = [
+        (lambda: eb.estimate_mi(y[:40], x), ValueError, "x and y must have same length"),
+        (lambda: eb.estimate_mi(y, np.zeros((50, 2, 2))), ValueError, "x must be one- or two-dimensional"),
+        (lambda: eb.estimate_mi(np.zeros((50, 2)), x), ValueError, "y must be one-dimensional"),
+        (lambda: eb.estimate_mi(y, x, cond=np.zeros(30)), ValueError, "x and cond must have same length"),
+        (lambda: eb.estimate_mi(y, x, k=0), ValueError, "k must be greater than zero"),
+        (lambda: eb.estimate_mi(y, x, k=3.0), TypeError, "k must be int"),
+        (lambda: eb.estimate_mi(y, x, k=50), ValueError, r"k must be smaller than number of observations \(after lag and mask\)"),
+        (lambda: eb.estimate_mi(y, x, lag=50), ValueError, "lag is too large, no observations left"),
+        (lambda: eb.estimate_mi(y, x, mask=np.ones(20, dtype=bool)), ValueError, "mask length does not match input length"),
+        (lambda: eb.estimate_mi(y, x, mask=np.ones(50)), TypeError, "mask must contain only booleans"),
+        (lambda: eb.estimate_mi(y, x, mask=np.ones((50, 2), dtype=bool)), ValueError, "mask must be one-dimensional"),
+        (lambda: eb.estimate_mi(y, np.where(x == 3, np.nan, x)), ValueError, "input contains NaNs"),
+        (lambda: eb.estimate_entropy(np.zeros((5, 2, 2))), ValueError, "x must be one- or two-dimensional"),
+        (lambda: eb.estimate_entropy(x, cond=np.zeros((50, 2, 2))), ValueError, "cond must be one- or two-dimensional"),
+        (lambda: eb.estimate_entropy(x, k=50), ValueError, "k must be smaller"),
+        (lambda: eb.pairwise_mi(np.column_stack((x, y)), discrete=[True, False], cond=x), ValueError, "Conditioning is not supported"),
+        (lambda: eb.estimate_mi(y, x, lag=1.5), TypeError, None),
+    ]
+    for fn, exc, msg in cases:
+        with pytest.raises(exc, match=msg):
+            fn()
+    with pytest.raises(ValueError, match="data must be finite"):
+        eb.estimate_mi(y, np.where(x == 3, np.inf, x), preprocess=False)
+
+
+def test_shapes_pandas_and_warnings(oracle_backend):
+    import pandas as pd
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame({"a": rng.normal(size=200), "b": rng.normal(size=200), "c": rng.normal(size=200)})
+    out = eb.estimate_mi(df["a"], df[["b", "c"]], lag=[0, 1])
+    assert isinstance(out, pd.DataFrame) and list(out.columns) == ["b", "c"] and list(out.index) == [0, 1]
+    out = eb.estimate_mi(df["a"], df["b"])
+    assert isinstance(out, pd.DataFrame) and list(out.columns) == ["b"]
+    pw = eb.pairwise_corr(df)
+    assert isinstance(pw, pd.DataFrame) and list(pw.index) == ["a", "b", "c"] and np.isnan(pw.loc["a", "a"])
+    assert pw.loc["a", "b"] == pw.loc["b", "a"]
+    ent = eb.estimate_entropy(df)
+    assert isinstance(ent, pd.DataFrame) and ent.shape == (1, 3)
+    assert np.asarray(eb.estimate_entropy(df, multidim=True)).shape == ()
+    assert isinstance(eb.normalize_mi(pw), pd.DataFrame)
+    assert eb.pairwise_mi(np.arange(10.0)).shape == (1, 1)
+    assert eb.estimate_mi(df["a"].values, df["b"].values).shape == (1, 1)
+    with pytest.warns(UserWarning, match="normalize=True while at least one variable is discrete"):
+        eb.estimate_mi(rng.integers(0, 3, 200), df["b"].values, discrete_y=True, normalize=True)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        eb.estimate_mi(df["a"].values, np.zeros(200) + 1e-30 * np.arange(200))
+    with pytest.warns(UserWarning, match="relatively many unique values"):
+        eb.estimate_mi(np.arange(200), df["b"].values, discrete_y=True)
+
+
+def test_callbacks_threads_and_determinism(oracle_backend, monkeypatch):
+    from ennemi_b200 import _schedule, _devices
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(300, 3)); y = x[:, 0] + rng.normal(size=300)
+    seen, threads = [], set()
+    lock = threading.Lock()
+
+    def cb(var, lag):
+        with lock:
+            seen.append((var, int(lag))); threads.add(threading.current_thread().name)
+
+    monkeypatch.setattr(_devices, "visible", lambda: [0, 1])       # pretend two GPUs: 4 worker threads
+    monkeypatch.setattr(_schedule, "INLINE_BUDGET_S", 0.0)
+    a = eb.estimate_mi(y, x, lag=[0, 1, -1], callback=cb)
+    assert sorted(seen) == sorted((v, l) for l in (0, 1, -1) for v in range(3))
+    assert any(t.startswith("ennemi-b200-work") for t in threads)
+    seen.clear()
+    b = eb.estimate_mi(y, x, lag=[0, 1, -1], max_threads=1, callback=cb)
+    assert len(seen) == 9 and eq(a, b)                              # same bits whatever the scheduling
+    pairs = []
+    c = eb.pairwise_mi(x, callback=lambda i, j: pairs.append((i, j)))
+    assert sorted(pairs) == [(0, 1), (0, 2), (1, 2)] and eq(c, c.T)
+
+    def boom(t):
+        raise ValueError("from a worker")
+    with pytest.raises(ValueError, match="from a worker"):
+        _schedule.run_tasks(boom, [1, 2, 3, 4], None, 1.0, lambda i: None)
+
+
+def test_seam_signatures_match_reference(oracle_backend):
+    """``ennemi/_driver.py:18-21`` imports these names; positional (x, y[, cond], k)."""
+    from ennemi_b200 import _estimators as e
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=400); y = x + rng.normal(size=400); z = rng.normal(size=(400, 2)); d = rng.integers(0, 3, 400)
+    import oracle
+    assert e._estimate_single_mi(x, y, 3) == oracle.ksg_mi(x, y, 3, backend="scipy")["value"]
+    assert e._estimate_conditional_mi(x, y, z, 3) == oracle.conditional_mi(x, y, z, 3, backend="scipy")["value"]
+    assert e._estimate_conditional_mi(x, y, z[:, 0], k=2) == oracle.conditional_mi(x, y, z[:, 0], 2, backend="scipy")["value"]
+    assert e._estimate_semidiscrete_mi(x, d, 3) == oracle.semidiscrete_mi(x, d, 3, backend="scipy")["value"]
+    assert e._estimate_conditional_semidiscrete_mi(x, d, z, 3) == oracle.conditional_semidiscrete_mi(x, d, z, 3, backend="scipy")["value"]
+    assert e._estimate_single_entropy(z, 3) == oracle.knn_entropy(z, 3, backend="scipy")["value"]
+    assert e._estimate_single_entropy(x[::2], 3) == oracle.knn_entropy(x[::2], 3, backend="scipy")["value"]   # strided view
+    assert np.isinf(e._psi(np.array([1, 0])))
