@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: KSG MI estimates/s at N = 10^6, k = 3 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one bivariate KSG estimate over the full 10^6-row synthetic Gaussian batch.  With N > 1
+(``torchrun``, one rank per GPU) the query rows of that one estimate are sharded over the ranks and
+the partial digamma sums are combined with one NCCL all-reduce ("strong" scaling: the work is fixed).
+
+Numbers on the JSON line:
+  value      estimates/s with the coordinates already resident in HBM (C ABI, EB2_FLAG_DEVICE_INPUT)
+  e2e        the same metric through the public API ``ennemi_b200.estimate_mi(y, x, k=3)`` on HOST
+             numpy buffers: host preprocessing + H2D + kernels + D2H inside the timed region
+  roofline   the dominant kernel (knn_kernel<2,4>) against the MEASURED FP64 issue rate
+  brute_force  the same step with EB2_FLAG_NO_PRUNE (every candidate tile visited): the kernel the
+             FP64 roofline in SURVEY.md §8(d) is defined on
+  cpu_baseline  the reference's CPU path (same SciPy cKDTree calls, via oracle/) on a bounded sample
+``--impl reference`` times only that CPU path and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "KSG MI estimates/sec at N=10^6, k=3"
+UNIT = "estimates/s"
+N_ROWS = 1_000_000
+K_NEIGH = 3
+RHO = 0.6
+FP64_OPS_PER_PAIR = 4          # 2-D space: 2 subtractions + 2 compares (2d per pair)
+SAMPLE_STRIDE = 20             # CPU baseline: every 20th row is queried, trees hold all rows
+
+
+def make_data(n=N_ROWS):
+    rng = np.random.default_rng(0)
+    d = rng.multivariate_normal([0, 0], [[1, RHO], [RHO, 1]], size=n)
+    return np.ascontiguousarray(d[:, 1]), np.ascontiguousarray(d[:, 0])     # estimate_mi(d[:,1], d[:,0])
+
+
+def preprocessed(y, x):
+    """The buffers the estimator sees inside estimate_mi(y, x): rescaled + fixed-seed noise."""
+    from ennemi_b200 import _align
+    xs, ys, _ = _align.rescaled(x, y, None, False, False)
+    return xs, ys
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own SciPy path (oracle "scipy" backend) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_step(xs, ys, k=K_NEIGH, stride=SAMPLE_STRIDE):
+    """Extrapolated seconds of one full estimate on the reference's SciPy path (oracle/timing.py)."""
+    from oracle import timing
+    return timing.ksg_mi_seconds(xs, ys, k, stride)
+
+
+def cpu_baseline_block(xs, ys, steps=1):
+    secs = [cpu_step(xs, ys) for _ in range(steps)]
+    best = min(secs)
+    return {"value": 1.0 / best, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle SciPy backend = the reference's cKDTree calls (_entropy_estimators.py:100-110): "
+                      f"3 trees on all {len(xs):,} rows, k-NN query + both marginal counts for every "
+                      f"{SAMPLE_STRIDE}th row, query time scaled x{SAMPLE_STRIDE}; a single estimate is one thread "
+                      f"in the reference (benchmarks/bench_large_sample_mi.py:6-7); host has {os.cpu_count()} cores",
+            "seconds_per_estimate": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    y, x = make_data()
+    xs, ys = preprocessed(y, x)
+    for _ in range(args.warmup):
+        cpu_step(xs, ys)
+    secs = [cpu_step(xs, ys) for _ in range(args.steps)]
+    per = sum(secs) / len(secs)
+    value = 1.0 / per
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1])",
+                   "n": N_ROWS, "k": K_NEIGH},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"oracle SciPy backend (the reference's cKDTree calls): trees on all rows, queries for "
+                                   f"every {SAMPLE_STRIDE}th row scaled x{SAMPLE_STRIDE}; single estimate = 1 thread in the reference"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, reasons, mx, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from ennemi_b200 import _native as nat, distributed as ebd, _devices
+    import ennemi_b200 as eb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    nat.require_device()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ebd.enable_row_sharding(True)
+
+    y, x = make_data()
+    xs, ys = preprocessed(y, x)
+    coords_host = nat.pack_coords([xs, ys])
+    coords_dev = torch.from_numpy(coords_host).to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(fn, steps, warmup):
+        """Each step bracketed by CUDA events on the current stream (every library call completes
+        before it returns), L2 flushed between steps outside the brackets; max over ranks."""
+        for _ in range(warmup):
+            fn()
+        total_ms, launches, knn_ms, pairs = 0.0, 0, 0.0, 0.0
+        for _ in range(steps):
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            extra = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            t = nat.last_timing(local)
+            launches += t["launches"]
+            knn_ms += t["knn_ms"]
+            if extra is not None:
+                pairs += extra
+        barrier()
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, launches, knn_ms, pairs
+
+    last = {}
+
+    def step_resident(flags=0):
+        rank_, size_ = ebd.world()
+        lo, hi = ebd.shard_bounds(N_ROWS, rank_, size_)
+        part = nat.ksg_mi_rows(int(coords_dev.data_ptr()), N_ROWS, K_NEIGH, lo, hi, dev=local,
+                               flags=flags | nat.FLAG_DEVICE_INPUT)
+        pairs = part[nat.P_PAIRS]
+        total = ebd._all_reduce_sum(part)
+        last["value"] = nat.ksg_mi_finish(total, N_ROWS, K_NEIGH)
+        return pairs
+
+    def step_e2e():
+        last["e2e"] = float(eb.estimate_mi(y, x, k=K_NEIGH)[0, 0])
+        return None
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_res, launches, knn_ms, pairs = timed_steps(step_resident, args.steps, args.warmup)
+    ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+
+    brute = None
+    if world == 1 and not args.no_brute:
+        bsteps = max(2, min(args.steps, 3))
+        ms_b, _, knn_b, pairs_b = timed_steps(lambda: step_resident(nat.FLAG_NO_PRUNE), bsteps, 1)
+        brute = (ms_b / bsteps, knn_b / bsteps, pairs_b / bsteps, last["value"])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak = nat.measure_fp64_peak(local)                                      # 1e12 FP64 instr/s, measured live
+    per_ms = ms_res / args.steps
+    knn_per_ms = knn_ms / args.steps
+    ops = pairs / args.steps * FP64_OPS_PER_PAIR                            # this rank's shard
+    achieved = ops / (knn_per_ms * 1e-3) * 1e-12
+    line = {
+        "metric": METRIC, "value": 1e3 / per_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]), "
+                               "query rows sharded over the GPUs, one all-reduce of the partial sums",
+                   "n": N_ROWS, "k": K_NEIGH, "algorithm": "exact sorted-window all-pairs (bit-exact eps and counts)",
+                   "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
+                   "parallelism": f"rows/{world}"},
+        "mi": last["value"],
+        "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(coords_host.nbytes), "d2h_bytes_per_step": 44,
+                "api": "ennemi_b200.estimate_mi(y, x, k=3) on host numpy arrays (host rescale+noise included)",
+                "mi": last.get("e2e")},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
+                     "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
+                             "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
+                             "ops = pairs actually evaluated x 4"},
+        "clocks": clocks,
+    }
+    if brute:
+        b_ms, b_knn, b_pairs, b_val = brute
+        b_ops = float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR
+        line["brute_force"] = {"value": 1e3 / b_ms, "ms_per_step": b_ms, "knn_ms": b_knn, "mi": b_val,
+                               "roofline": {"bound": "fp64", "achieved": b_ops / (b_knn * 1e-3) * 1e-12, "peak": peak,
+                                            "unit": "TFLOP/s", "frac": b_ops / (b_knn * 1e-3) * 1e-12 / peak,
+                                            "ops_per_launch": b_ops}}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_block(xs, ys, 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-brute", action="store_true", help="skip the brute-force (EB2_FLAG_NO_PRUNE) leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -4,7 +4,9 @@ buffers this module produces are "the same preprocessed inputs" the parity contr
 """
 from __future__ import annotations
 
+import threading
 import warnings
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -86,11 +88,51 @@ def validate(xs, ys, zs, t: MiTask) -> None:
         raise ValueError(_checks.MSG_NANS_LEFT)
 
 
+class _NoiseStream:
+    """The reference draws its noise from ``default_rng(2718281828)`` created afresh for every
+    task, so the values depend only on the sequence of draw shapes.  Tasks of one call repeat the
+    same sequence thousands of times; the draws are memoised per shape sequence (bit-identical,
+    small LRU) instead of regenerating ~N Gaussians per variable per task."""
+
+    _cache: "OrderedDict[tuple, np.ndarray]" = OrderedDict()
+    _lock = threading.Lock()
+    MAX_BYTES = 1 << 28
+
+    def __init__(self):
+        self._shapes = ()
+        self._rng = None
+
+    def normal(self, shape) -> np.ndarray:
+        shape = tuple(shape)
+        key = self._shapes + (shape,)
+        with self._lock:
+            hit = self._cache.get(key)
+            if hit is not None:
+                self._cache.move_to_end(key)
+        if hit is None:
+            if self._rng is None:                     # replay the earlier draws to reach the stream position
+                self._rng = np.random.default_rng(NOISE_SEED)
+                for sh in self._shapes:
+                    self._rng.normal(0.0, NOISE_SCALE, sh)
+            hit = self._rng.normal(0.0, NOISE_SCALE, shape)
+            hit.setflags(write=False)
+            with self._lock:
+                self._cache[key] = hit
+                total = sum(a.nbytes for a in self._cache.values())
+                while total > self.MAX_BYTES and len(self._cache) > 1:
+                    _, old = self._cache.popitem(last=False)
+                    total -= old.nbytes
+        elif self._rng is not None:
+            self._rng.normal(0.0, NOISE_SCALE, shape)  # keep a live generator in step
+        self._shapes = key
+        return hit
+
+
 def rescaled(xs, ys, zs, discrete_x: bool, discrete_y: bool):
     """Unit variance plus N(0, 1e-10) noise from a fixed-seed generator; draw order x, y, z;
     discrete variables consume no draws; (near-)constant data is left alone with a warning
     (``_driver.py:871-902``)."""
-    rng = np.random.default_rng(NOISE_SEED)
+    rng = _NoiseStream()
 
     def one(v):
         spread = v.std()
@@ -98,7 +140,7 @@ def rescaled(xs, ys, zs, discrete_x: bool, discrete_y: bool):
             warnings.warn(CONSTANT_DATA_WARNING)
             return v
         v = (v - v.mean()) / spread
-        v += rng.normal(0.0, NOISE_SCALE, v.shape)
+        v += rng.normal(v.shape)
         return v
 
     if not discrete_x:
@@ -111,7 +153,7 @@ def rescaled(xs, ys, zs, discrete_x: bool, discrete_y: bool):
             warnings.warn(CONSTANT_DATA_WARNING)
         else:
             zs = (zs - zs.mean(axis=0)) / spread
-            zs += rng.normal(0.0, NOISE_SCALE, zs.shape)
+            zs += rng.normal(zs.shape)
     return xs, ys, zs
 
 

@@ -44,17 +44,29 @@ def _classes(y):
 def _estimate_single_entropy(x, k: int = 3) -> float:
     """Kozachenko-Leonenko entropy in nats; replaces ``_entropy_estimators.py:21-42``.
     ``x`` is (n,) or (n, m), one row per observation."""
-    return _native.entropy(_coords(np.asarray(x)), k, dev=_devices.current())
+    coords = _coords(np.asarray(x))
+    from . import distributed
+    if distributed.row_sharding_enabled():
+        return distributed.sharded_entropy(coords, k)
+    return _native.entropy(coords, k, dev=_devices.current())
 
 
 def _estimate_single_mi(x, y, k: int = 3) -> float:
     """KSG mutual information in nats; replaces ``_entropy_estimators.py:69-113``."""
-    return _native.ksg_mi(_coords(np.asarray(x), np.asarray(y)), k, dev=_devices.current())
+    coords = _coords(np.asarray(x), np.asarray(y))
+    from . import distributed
+    if distributed.row_sharding_enabled():      # one process per GPU: shard the query rows, one all-reduce
+        return distributed.sharded_ksg_mi(coords, k)
+    return _native.ksg_mi(coords, k, dev=_devices.current())
 
 
 def _estimate_conditional_mi(x, y, cond, k: int = 3) -> float:
     """Frenzel-Pompe conditional MI; replaces ``_entropy_estimators.py:116-156``."""
-    return _native.cmi(_coords(np.asarray(x), np.asarray(y), np.asarray(cond)), k, dev=_devices.current())
+    coords = _coords(np.asarray(x), np.asarray(y), np.asarray(cond))
+    from . import distributed
+    if distributed.row_sharding_enabled():
+        return distributed.sharded_cmi(coords, k)
+    return _native.cmi(coords, k, dev=_devices.current())
 
 
 def _estimate_semidiscrete_mi(x, y, k: int = 3) -> float:

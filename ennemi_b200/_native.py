@@ -30,7 +30,7 @@ EXPORTS = (
     "eb2_cmi", "eb2_cmi_rows", "eb2_cmi_finish",
     "eb2_ross_mi", "eb2_ross_cmi",
     "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
-    "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing",
+    "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
 )
 
 _lib = None
@@ -75,6 +75,7 @@ def load():
         lib.eb2_kth_distance.argtypes = [_int, _vp, _vp, _i64, _int, _int, _int, _u32, _vp]
         lib.eb2_ball_count.argtypes = [_int, _vp, _vp, _i64, _int, _int, _int, _vp, _u32, _vp]
         lib.eb2_last_timing.argtypes = [_int, _c_dp, ctypes.POINTER(_int)]
+        lib.eb2_measure_fp64_peak.argtypes = [_int, _c_dp]
         for name in EXPORTS:
             getattr(lib, name)
         _lib = lib
@@ -290,3 +291,13 @@ def last_timing(dev: int = 0) -> dict:
         _raise(rc)
     return {"total_ms": ms[0], "knn_ms": ms[1], "count_ms": ms[2], "psi_ms": ms[3], "layout_ms": ms[4],
             "launches": launches.value}
+
+
+def measure_fp64_peak(dev: int = 0) -> float:
+    """FP64 (DADD) issue rate of the device in 1e12 instructions/s — the roofline denominator."""
+    lib = load()
+    out = ctypes.c_double()
+    rc = lib.eb2_measure_fp64_peak(dev, ctypes.byref(out))
+    if rc:
+        _raise(rc)
+    return out.value

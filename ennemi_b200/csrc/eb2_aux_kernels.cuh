@@ -191,4 +191,15 @@ __global__ void nonfinite_kernel(const double* v, int64_t count, int* flag) {
   }
 }
 
+
+// register-resident DADD chains: the FP64 issue rate that bounds the all-pairs kernels
+__global__ void fp64_peak_kernel(double* out, double c, int iters) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  for (int it = 0; it < iters; ++it) {
+    a0 = __dadd_rn(a0, c); a1 = __dadd_rn(a1, c); a2 = __dadd_rn(a2, c); a3 = __dadd_rn(a3, c);
+    a4 = __dadd_rn(a4, c); a5 = __dadd_rn(a5, c); a6 = __dadd_rn(a6, c); a7 = __dadd_rn(a7, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace eb2

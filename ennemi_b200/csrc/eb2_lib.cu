@@ -830,6 +830,29 @@ int eb2_psi(int dev, const int64_t* counts, int64_t n, double* out) {
   });
 }
 
+// ---- roofline denominator: measured FP64 (DADD) issue rate of this device -----------------------------
+int eb2_measure_fp64_peak(int dev, double* tera_instr_per_s) {
+  if (!tera_instr_per_s) return fail(EB2_ERR_ARG, "output is NULL");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    const int blocks = c.sm_count * 32, threads = 256, iters = 4096;
+    double* out = s.dev<double>(static_cast<size_t>(blocks) * threads);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      CU(cudaEventRecord(c.ev[6], c.stream));
+      fp64_peak_kernel<<<blocks, threads, 0, c.stream>>>(out, 1e-9, iters);
+      CU(cudaEventRecord(c.ev[7], c.stream));
+      CU(cudaStreamSynchronize(c.stream));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, c.ev[6], c.ev[7]));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    *tera_instr_per_s = 8.0 * iters * static_cast<double>(blocks) * threads / (best * 1e-3) * 1e-12;
+    return EB2_OK;
+  });
+}
+
 // ---- primitives ---------------------------------------------------------------------------------------------
 int eb2_kth_distance(int dev, const double* coords, const int32_t* cls, int64_t n, int d, int ncls, int k,
                      uint32_t flags, double* out) {

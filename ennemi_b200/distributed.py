@@ -51,6 +51,21 @@ def enable_task_fanout(on: bool = True) -> None:
     _enabled = on
 
 
+_row_sharding = False
+
+
+def enable_row_sharding(on: bool = True) -> None:
+    """Make every single KSG / CMI / entropy estimate shard its query rows over the ranks (every
+    rank must make the same call with the same data).  Use for a few very large estimates; for
+    many small tasks prefer :func:`enable_task_fanout`."""
+    global _row_sharding
+    _row_sharding = on
+
+
+def row_sharding_enabled() -> bool:
+    return _row_sharding and is_initialized() and world()[1] > 1
+
+
 def task_fanout_enabled() -> bool:
     return _enabled and is_initialized() and world()[1] > 1
 

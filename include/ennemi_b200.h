@@ -128,6 +128,10 @@ EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, in
  * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
 EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
 
+/* roofline denominator: FP64 (DADD) instructions per second this device retires, in 10^12/s,
+ * measured with a register-resident kernel (best of 5).  The all-pairs kernels are bound by it. */
+EB2_API int eb2_measure_fp64_peak(int dev, double* tera_instr_per_s);
+
 #ifdef __cplusplus
 }
 #endif

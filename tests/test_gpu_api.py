@@ -1,0 +1,106 @@
+"""The public API end to end on the GPU against the reference's outputs (``tests/golden/api.npz``)
+— tolerance 1e-10 absolute on every MI / entropy value (north_star) — plus the reference's
+bitwise-determinism contract (``tests/unit/test_driver.py:921-923, 989-990, 1555-1557``)."""
+import warnings
+
+import numpy as np
+import pytest
+
+import ennemi_b200 as eb
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def near(a, b, tol=TOL):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    with np.errstate(invalid="ignore"):
+        return a.shape == b.shape and bool(np.all(same | (np.abs(a - b) <= tol)))
+
+
+def test_api_cases_match_reference_outputs(golden_api):
+    g = golden_api
+    x3, y, cond, mask, lags = (g["inputs"][k] for k in ("x3", "y", "cond", "mask", "lags"))
+    yd, xd = g["mi_discrete_y"]["yd"], g["mi_discrete_x"]["xd"]
+    ynan, xnan = g["mi_dropnan"]["ynan"], g["mi_dropnan"]["xnan"]
+    data5 = np.column_stack((x3, y, cond[:, 0]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert near(eb.estimate_mi(y, x3, lags), g["mi_lags"]["out"])
+        assert near(eb.estimate_mi(y, x3, lags, k=5, preprocess=False), g["mi_lags_k5_nopre"]["out"])
+        assert near(eb.estimate_mi(y, x3[:, :2], lags, cond=cond), g["mi_cond"]["out"])
+        assert near(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=1), g["mi_cond_lag1"]["out"])
+        assert near(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=g["mi_cond_lag2d"]["cond_lag"]), g["mi_cond_lag2d"]["out"])
+        assert near(eb.estimate_mi(y, x3, lags, mask=mask), g["mi_mask"]["out"])
+        assert near(eb.estimate_mi(y, x3[:, 0], [0, 2], mask=mask, cond=cond[:, 0]), g["mi_mask_cond"]["out"])
+        assert near(eb.estimate_corr(y, x3, lags), g["corr_lags"]["out"])
+        assert near(eb.estimate_mi(ynan, xnan, [0, 1], drop_nan=True), g["mi_dropnan"]["out"])
+        assert near(eb.estimate_mi(yd, x3, [0, 2], discrete_y=True), g["mi_discrete_y"]["out"])
+        assert near(eb.estimate_mi(y, xd, [0, 2], discrete_x=True, k=4), g["mi_discrete_x"]["out"])
+        assert near(eb.estimate_mi(yd, x3[:, :2], [0, 1], discrete_y=True, cond=cond), g["mi_discrete_y_cond"]["out"])
+        assert near(eb.estimate_mi(y, xd, [0, 1], discrete_x=True, cond=cond[:, 0]), g["mi_discrete_x_cond"]["out"])
+        assert near(eb.estimate_mi(yd, xd, [0, 1], discrete_x=True, discrete_y=True), g["mi_discrete_both"]["out"])
+        assert near(eb.pairwise_mi(x3), g["pairwise"]["out"])
+        assert near(eb.pairwise_mi(data5, k=4), g["pairwise5"]["out"])
+        assert near(eb.pairwise_corr(data5), g["pairwise5_corr"]["out"])
+        assert near(eb.pairwise_mi(np.column_stack((x3, y)), cond=cond, mask=mask), g["pairwise_cond_mask"]["out"])
+        assert near(eb.pairwise_mi(np.column_stack((x3[:, 0], xd, yd, y)), discrete=[False, True, True, False]), g["pairwise_discrete"]["out"])
+        assert near(eb.pairwise_mi(np.column_stack((xnan, ynan)), drop_nan=True), g["pairwise_dropnan"]["out"])
+        assert near(eb.estimate_entropy(x3), g["ent_cols"]["out"])
+        assert near(eb.estimate_entropy(x3, multidim=True, k=5), g["ent_multidim"]["out"])
+        assert near(eb.estimate_entropy(x3[:, :2], cond=cond), g["ent_cond"]["out"])
+        assert near(eb.estimate_entropy(x3[:, :2], cond=cond[:, 0], multidim=True, mask=mask), g["ent_cond_multidim_mask"]["out"])
+        assert near(eb.estimate_entropy(ynan, drop_nan=True), g["ent_1d_dropnan"]["out"])
+
+
+def test_docs_known_answers_on_gpu(golden_api):
+    g = golden_api
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0, 0], [[1, 0.8], [0.8, 1]], size=800)
+    z = rng.normal(0, 1, size=800)
+    out = eb.estimate_corr(data[:, 1], np.column_stack((data[:, 0], z)))
+    assert near(out, g["doc_tutorial_165"]["out"]) and near(out, g["doc_tutorial_165"]["printed"], 5e-9)
+    rng = np.random.default_rng(1234)
+    x = rng.gamma(1.0, 1.0, size=400); y = np.zeros(400); y[1:] = x[0:-1]; y += rng.normal(0, 0.01, size=400)
+    assert near(eb.estimate_corr(y, x, lag=[1, 0, -1]), g["doc_tutorial_208"]["printed"], 5e-9)
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0, 0], [[1, 0.8], [0.8, 1]], size=800)
+    assert near(eb.estimate_mi(np.exp(data[:, 1]), np.exp(5 * data[:, 0])), g["doc_issues_68"]["printed"], 5e-9)
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0.5, 0.5], [[1, 0.8], [0.8, 1]], size=800)
+    assert eb.estimate_mi(np.maximum(0, data[:, 1]), np.maximum(0, data[:, 0]), preprocess=False)[0, 0] == -np.inf
+    rng = np.random.default_rng(1234)
+    data = rng.multivariate_normal([0, 0], [[1, 0.8], [0.8, 1]], size=800)
+    x = np.concatenate((data[:, 0], data[:, 0] + rng.normal(0, 0.01, size=800), data[:, 0] + rng.normal(0, 0.01, size=800)))
+    y = np.concatenate((data[:, 1], data[:, 1] + rng.normal(0, 0.01, size=800), data[:, 1] + rng.normal(0, 0.01, size=800)))
+    assert near(eb.estimate_mi(y, x), g["doc_issues_168"]["printed"], 5e-9)
+
+
+def test_bitwise_determinism_contract():
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(3_000, 4)); y = x[:, 0] + rng.normal(size=3_000)
+    a = eb.estimate_mi(y, x, lag=[0, 1, 2])
+    b = eb.estimate_mi(y, x, lag=[0, 1, 2], max_threads=1)
+    assert np.array_equal(a, b)                                             # scheduling never changes bits
+    assert np.array_equal(eb.estimate_corr(y, x), eb.estimate_mi(y, x, normalize=True))
+    pw = eb.pairwise_mi(x)
+    assert np.array_equal(pw, pw.T, equal_nan=True)
+    d = rng.integers(0, 4, 3_000)
+    m1 = eb.estimate_mi(d, y, discrete_y=True)
+    m2 = eb.estimate_mi(y, d, discrete_x=True)
+    assert m1[0, 0] == m2[0, 0]                                             # x<->y symmetry with a discrete variable
+
+
+def test_analytic_values():
+    """The reference's statistical tests in miniature: Gaussian MI, CMI chain, uniform entropy."""
+    rng = np.random.default_rng(0)
+    for rho in (0.0, 0.5, 0.9):
+        d = rng.multivariate_normal([0, 0], [[1, rho], [rho, 1]], size=20_000)
+        mi = eb.estimate_mi(d[:, 1], d[:, 0])[0, 0]
+        assert abs(mi - (-0.5 * np.log(1 - rho ** 2))) < 0.03
+    u = rng.uniform(0, 2, size=20_000)
+    assert abs(float(eb.estimate_entropy(u)) - np.log(2)) < 0.02
+    z = rng.normal(size=20_000); x = z + rng.normal(size=20_000) * 0.5; y = z + rng.normal(size=20_000) * 0.5
+    assert abs(eb.estimate_mi(y, x, cond=z)[0, 0]) < 0.02                   # conditionally independent
+    assert eb.estimate_mi(y, x)[0, 0] > 0.3
