@@ -38,6 +38,16 @@ __device__ __forceinline__ void stage_chunk(double* sbuf, uint64_t* bar, const d
 // ----------------------------------------------------------------------------------------------
 // (1) k-th neighbour distance
 // ----------------------------------------------------------------------------------------------
+// a query whose search was cut short: candidates still to be examined are the segment slots
+// [c_lo + rstart, c_lo + c_len) on the right and [c_lo, c_lo + lend) on the left
+struct LeftEntry {
+  int slot;     // query slot in P
+  int c_lo;
+  int c_len;
+  int rstart;   // == c_len: nothing left on the right
+  int lend;     // == 0: nothing left on the left
+};
+
 struct KnnArgs {
   const double* P;       // padded dimension-major point set
   int64_t stride;        // slots per row
@@ -49,16 +59,25 @@ struct KnnArgs {
   double* heap;          // scratch for the large-k variant: [k+1][gridDim.x * kTileQ]
   unsigned long long* pairs;  // work counter (pairs evaluated)
   int ntiles;
+  // straggler deferral (pruned mode, register top-k variants): when fewer than `defer_below` threads of a
+  // CTA still need candidate chunks in a direction, their queries are appended to `left_list` (with
+  // their current lists in `left_best`) and finished by knn_leftover_kernel, one warp per query.
+  int defer_below;
+  struct LeftEntry* left_list;
+  unsigned int* left_count;
+  double* left_best;     // [slot][K1T]
 };
 
-// sorted ascending register list; precondition v < best[K1T-1]
+// sorted ascending register list; precondition v < best[K1T-1].  No NaNs can reach here (a NaN
+// distance never passes the `<` test), so plain compare+select is enough (no fmin/fmax NaN fix-ups).
 template <int K1T>
 __device__ __forceinline__ void topk_insert(double (&best)[K1T], double v) {
   best[K1T - 1] = v;
 #pragma unroll
   for (int t = K1T - 1; t > 0; --t) {
-    const double lo = fmin(best[t - 1], best[t]);
-    const double hi = fmax(best[t - 1], best[t]);
+    const bool sw = best[t] < best[t - 1];
+    const double lo = sw ? best[t] : best[t - 1];
+    const double hi = sw ? best[t - 1] : best[t];
     best[t - 1] = lo;
     best[t] = hi;
   }
@@ -68,7 +87,10 @@ template <int D>
 __device__ __forceinline__ double cheb(const double (&q)[D], const double (&c)[D]) {
   double m = fabs(q[0] - c[0]);
 #pragma unroll
-  for (int t = 1; t < D; ++t) m = fmax(m, fabs(q[t] - c[t]));
+  for (int t = 1; t < D; ++t) {
+    const double v = fabs(q[t] - c[t]);
+    m = (v > m) ? v : m;
+  }
   return m;
 }
 
@@ -111,14 +133,48 @@ struct HeapRef {
   }
 };
 
+// ---- in-CTA reordering of the tile's queries -------------------------------------------------------
+// Bitonic sort of the kTileQ per-query keys (ascending) in shared memory; afterwards rank r holds the
+// home index sidx[r] of the query with the r-th smallest key.  Used to make warps homogeneous in
+// search radius so that whole warps can skip candidate chunks (exact pruning at warp granularity).
+__device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
+  const int tid = threadIdx.x;
+  for (int k = 2; k <= kTileQ; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int i = 2 * j * (tid / j) + (tid % j);
+      const int l = i + j;
+      const bool up = (i & k) == 0;
+      const double a = skey[i], b = skey[l];
+      if ((a > b) == up) {
+        skey[i] = b; skey[l] = a;
+        const int t = sidx[i]; sidx[i] = sidx[l]; sidx[l] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// moves one per-query double from its home thread to the thread that owns the query after sorting
+__device__ __forceinline__ void cta_permute(double* xch, const int (&src)[kQpt], double (&v)[kQpt]) {
+#pragma unroll
+  for (int i = 0; i < kQpt; ++i) xch[threadIdx.x + i * kThreads] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kQpt; ++i) v[i] = xch[src[i]];
+  __syncthreads();
+}
+
+constexpr int kGroup = 4;   // candidates tested per branch in the all-pairs inner loops
+
 // K1T > 0: register-resident sorted top-K1T (k+1 <= K1T).  K1T == 0: heap in global scratch, any k.
 template <int D, int K1T>
 __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const KnnArgs a) {
   constexpr int TC = chunk_len(D);
   constexpr int NB = (K1T > 0 ? K1T : 1);
   __shared__ __align__(128) double sbuf[D * TC];
+  __shared__ __align__(16) double xch[kTileQ];
+  __shared__ int sidx[kTileQ];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ double red[kThreads / 32 + 1];
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -136,11 +192,16 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
     double q[kQpt][D];
     double best[kQpt][NB];
     double thr[kQpt];
+    int qslot[kQpt];          // position of the query inside the tile
+    int rstart[kQpt], lend[kQpt];   // deferred remainder of the search (segment-relative slots)
     bool valid[kQpt];
     HeapRef heap[kQpt];
 #pragma unroll
     for (int i = 0; i < kQpt; ++i) {
       const int qi = tid + i * kThreads;
+      qslot[i] = qi;
+      rstart[i] = tile.c_len;
+      lend[i] = 0;
       valid[i] = qi < tile.q_n;
 #pragma unroll
       for (int t = 0; t < D; ++t)
@@ -158,51 +219,36 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
 
     const int len_pad = (tile.c_len + kSegAlign - 1) / kSegAlign * kSegAlign;
     const int nchunks = (len_pad + TC - 1) / TC;
-    const bool prune = a.sort_row >= 0;
-    int home_lo = 0, home_hi = nchunks - 1;
-    double q0min = 0.0, q0max = 0.0;
-    if (prune) {
-      home_lo = (tile.q_lo - tile.c_lo) / TC;
-      home_hi = (tile.q_lo - tile.c_lo + tile.q_n - 1) / TC;
-      q0min = a.P[a.sort_row * a.stride + tile.q_lo];
-      q0max = a.P[a.sort_row * a.stride + tile.q_lo + tile.q_n - 1];
-    }
+    const bool prune = a.sort_row >= 0;      // then rows.row[0] == sort_row (host guarantees it)
     unsigned long long npairs = 0;
 
-    // visit order: home chunks, then rightwards, then leftwards; a direction stops as soon as the
-    // gap in the sorted coordinate is >= every query's current k-th distance (exact: rounding is monotone)
-    int j = home_lo;
-    int dir = +1;
-    while (true) {
-      const int c_off = j * TC;
-      const int len = min(TC, len_pad - c_off);
-      if (tid == 0) stage_chunk<D, TC>(sbuf, &bar, a.P, a.stride, a.rows, tile.c_lo + c_off, len);
-      mbar_wait(&bar, phase);
-      phase ^= 1;
-      npairs += (unsigned long long)min(TC, tile.c_len - c_off);
-
-#pragma unroll 2
-      for (int jj = 0; jj < len; jj += 2) {
-        double c0[D], c1[D];
+    // all queries of this thread against one staged chunk
+    auto scan_chunk = [&](int len) {
+#pragma unroll 1
+      for (int jj = 0; jj < len; jj += kGroup) {
+        double c[kGroup][D];
 #pragma unroll
         for (int t = 0; t < D; ++t) {
-          const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj]);
-          c0[t] = v.x;
-          c1[t] = v.y;
+#pragma unroll
+          for (int u = 0; u < kGroup; u += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj + u]);
+            c[u][t] = v.x;
+            c[u + 1][t] = v.y;
+          }
         }
+        bool any = false;
 #pragma unroll
         for (int i = 0; i < kQpt; ++i) {
-          const bool h0 = inside_lt<D>(q[i], c0, thr[i]);
-          const bool h1 = inside_lt<D>(q[i], c1, thr[i]);
-          if (h0 | h1) {
-            if (h0) {
-              const double m = cheb<D>(q[i], c0);
-              if constexpr (K1T > 0) { topk_insert<K1T>(best[i], m); thr[i] = best[i][K1T - 1]; }
-              else thr[i] = heap[i].replace_root(m);
-            }
-            if (h1) {
-              const double m = cheb<D>(q[i], c1);
-              if (m < thr[i]) {
+#pragma unroll
+          for (int u = 0; u < kGroup; ++u) any = any | inside_lt<D>(q[i], c[u], thr[i]);
+        }
+        if (any) {   // some lane has a new neighbour: re-test pair by pair (the k-th distance moves)
+#pragma unroll
+          for (int u = 0; u < kGroup; ++u) {
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i) {
+              if (inside_lt<D>(q[i], c[u], thr[i])) {
+                const double m = cheb<D>(q[i], c[u]);
                 if constexpr (K1T > 0) { topk_insert<K1T>(best[i], m); thr[i] = best[i][K1T - 1]; }
                 else thr[i] = heap[i].replace_root(m);
               }
@@ -210,35 +256,123 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
           }
         }
       }
-      __syncthreads();  // everyone is done with sbuf before the next bulk copy lands in it
+    };
+    auto fetch_chunk = [&](int j) -> int {
+      const int c_off = j * TC;
+      const int len = min(TC, len_pad - c_off);
+      if (tid == 0) stage_chunk<D, TC>(sbuf, &bar, a.P, a.stride, a.rows, tile.c_lo + c_off, len);
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      return len;
+    };
 
-      // pick the next chunk (uniform across the CTA)
-      if (dir > 0) {
-        bool go = j + 1 < nchunks;
-        if (go && prune && j + 1 > home_hi) {
-          double tmax = 0.0;
-#pragma unroll
-          for (int i = 0; i < kQpt; ++i) tmax = fmax(tmax, valid[i] ? thr[i] : 0.0);
-          tmax = block_max_bcast<kThreads>(tmax, red);
-          const double cmin = a.P[a.sort_row * a.stride + tile.c_lo + (j + 1) * TC];
-          go = !((cmin - q0max) >= tmax);
-        }
-        if (go) { ++j; continue; }
-        dir = -1;
-        j = home_lo;
+    if (!prune) {
+      for (int j = 0; j < nchunks; ++j) {
+        const int len = fetch_chunk(j);
+        if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
+        scan_chunk(len);
+        __syncthreads();   // everyone is done with sbuf before the next bulk copy lands in it
       }
-      {
-        bool go = j - 1 >= 0;
-        if (go && prune) {
-          double tmax = 0.0;
+    } else {
+      // 1. the chunks that overlap the tile itself: seeds every list with near neighbours
+      const int home_lo = (tile.q_lo - tile.c_lo) / TC;
+      const int home_hi = (tile.q_lo - tile.c_lo + tile.q_n - 1) / TC;
+      for (int j = home_lo; j <= home_hi; ++j) {
+        const int len = fetch_chunk(j);
+        if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
+        scan_chunk(len);
+        __syncthreads();
+      }
+      if (home_lo > 0 || home_hi + 1 < nchunks) {
+        // 2. regroup the tile's queries by current k-th distance: warp w gets ranks [64w, 64w+64)
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) tmax = fmax(tmax, valid[i] ? thr[i] : 0.0);
-          tmax = block_max_bcast<kThreads>(tmax, red);
-          const double cmax = a.P[a.sort_row * a.stride + tile.c_lo + min(j * TC, tile.c_len) - 1];
-          go = !((q0min - cmax) >= tmax);
+        for (int i = 0; i < kQpt; ++i) {
+          xch[tid + i * kThreads] = valid[i] ? thr[i] : 0.0;
+          sidx[tid + i * kThreads] = tid + i * kThreads;
         }
-        if (!go) break;
-        --j;
+        __syncthreads();
+        cta_sort_keys(xch, sidx);
+        int src[kQpt];
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) src[i] = sidx[kQpt * tid + i];
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < D; ++t) {
+          double v[kQpt];
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) v[i] = q[i][t];
+          cta_permute(xch, src, v);
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) q[i][t] = v[i];
+        }
+        if constexpr (K1T > 0) {
+#pragma unroll
+          for (int t = 0; t < K1T; ++t) {
+            double v[kQpt];
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i) v[i] = best[i][t];
+            cta_permute(xch, src, v);
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i) best[i][t] = v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) thr[i] = best[i][K1T - 1];
+        } else {
+          cta_permute(xch, src, thr);
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) heap[i].base = a.heap + (int64_t)blockIdx.x * kTileQ + src[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) {
+          qslot[i] = src[i];
+          valid[i] = src[i] < tile.q_n;
+        }
+        // 3. outwards; a query needs chunk j only while the gap to the chunk in the sorted coordinate is
+        //    below its current k-th distance (rounded subtraction is monotone => exact); a warp scans
+        //    the chunk iff one of its queries needs it; the CTA stops when no warp does.
+        const double* srow = a.P + a.sort_row * a.stride + tile.c_lo;
+        for (int j = home_hi + 1; j < nchunks; ++j) {
+          const double cmin = srow[j * TC];
+          bool need = false;
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) need = need || (valid[i] && !((cmin - q[i][0]) >= thr[i]));
+          const bool wneed = __any_sync(0xffffffffu, need);
+          const int nneed = __syncthreads_count(need);
+          if (nneed == 0) break;
+          if (nneed < a.defer_below) {   // stragglers: hand the rest of this direction to the leftover kernel
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i)
+              if (valid[i] && !((cmin - q[i][0]) >= thr[i])) rstart[i] = j * TC;
+            break;
+          }
+          const int len = fetch_chunk(j);
+          if (wneed) {
+            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
+            scan_chunk(len);
+          }
+        }
+        __syncthreads();
+        for (int j = home_lo - 1; j >= 0; --j) {
+          const double cmax = srow[min((j + 1) * TC, tile.c_len) - 1];
+          bool need = false;
+#pragma unroll
+          for (int i = 0; i < kQpt; ++i) need = need || (valid[i] && !((q[i][0] - cmax) >= thr[i]));
+          const bool wneed = __any_sync(0xffffffffu, need);
+          const int nneed = __syncthreads_count(need);
+          if (nneed == 0) break;
+          if (nneed < a.defer_below) {
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i)
+              if (valid[i] && !((q[i][0] - cmax) >= thr[i])) lend[i] = min((j + 1) * TC, tile.c_len);
+            break;
+          }
+          const int len = fetch_chunk(j);
+          if (wneed) {
+            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
+            scan_chunk(len);
+          }
+        }
+        __syncthreads();
       }
     }
 
@@ -253,11 +387,137 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
         } else {
           r = thr[i];
         }
-        a.eps[tile.q_lo + tid + i * kThreads] = r;
+        a.eps[tile.q_lo + qslot[i]] = r;
+        if constexpr (K1T > 0) {
+          if (rstart[i] < tile.c_len || lend[i] > 0) {
+            const unsigned int e = atomicAdd(a.left_count, 1u);
+            LeftEntry le;
+            le.slot = tile.q_lo + qslot[i]; le.c_lo = tile.c_lo; le.c_len = tile.c_len;
+            le.rstart = rstart[i]; le.lend = lend[i];
+            a.left_list[e] = le;
+#pragma unroll
+            for (int t = 0; t < K1T; ++t) a.left_best[(int64_t)le.slot * K1T + t] = best[i][t];
+          }
+        }
       }
     }
-    if (tid == 0 && a.pairs) atomicAdd(a.pairs, npairs * (unsigned long long)tile.q_n);
+    if (a.pairs) {
+      // per-thread pair counts: thread 0 carries the CTA-wide phases, lane 0 of each warp its own chunks
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+      if ((tid & 31) == 0 && npairs) atomicAdd(a.pairs, npairs);
+    }
   }
+}
+
+// first slot s in [lo, hi) of an ascending coordinate array with pred(s) true, pred monotone
+// (false ... false true ... true); all 32 lanes cooperate: 32 probes per round, ~4 rounds for 10^6 slots
+template <typename Pred>
+__device__ __forceinline__ int warp_first_true(int lo, int hi, Pred pred) {
+  const int lane = threadIdx.x & 31;
+  while (hi - lo > 32) {
+    const int step = (hi - lo + 32) / 33;             // probes at lo + step*(lane+1) - 1
+    const int pos = min(lo + step * (lane + 1) - 1, hi - 1);
+    const unsigned int m = __ballot_sync(0xffffffffu, pred(pos));
+    if (m == 0) { lo = min(lo + step * 32, hi); if (lo >= hi) return hi; continue; }
+    const int f = __ffs(m) - 1;                        // first probing lane whose slot satisfies pred
+    hi = min(lo + step * (f + 1) - 1, hi - 1) + 1;
+    lo = lo + step * f;
+  }
+  const int pos = lo + lane;
+  const unsigned int m = __ballot_sync(0xffffffffu, pos < hi && pred(pos));
+  return m ? lo + (__ffs(m) - 1) : hi;
+}
+
+// pops the k1 smallest values held across the lanes' sorted lists (K1T each); returns the r-th popped
+// value in lane r (for r < k1, k1 <= 32) — i.e. the merged sorted list, one element per lane
+template <int K1T>
+__device__ __forceinline__ double warp_merge_lists(const double (&best)[K1T], int k1) {
+  const int lane = threadIdx.x & 31;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  int head = 0;
+  double out = kInf;
+  for (int r = 0; r < k1; ++r) {
+    double mine = kInf;
+#pragma unroll
+    for (int t = 0; t < K1T; ++t) mine = (t == head) ? best[t] : mine;
+    double mn = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    const unsigned int who = __ballot_sync(0xffffffffu, mine == mn && head < K1T);
+    if (who != 0 && lane == __ffs(who) - 1) ++head;
+    if (lane == r) out = mn;
+  }
+  return out;
+}
+
+// One CTA per deferred query: the 256 threads share out the remaining candidates (coalesced loads
+// straight from L2, four independent candidates per thread per step), each keeps a private sorted
+// top-K1T gated by the query's current k-th distance; the lists are merged per warp, then across the
+// warps together with the list the main kernel left behind.  Same exact tests, same order statistic.
+template <int D, int K1T>
+__global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a) {
+  constexpr int U = 4;
+  constexpr int NW = kThreads / 32;
+  __shared__ double wlist[NW + 1][K1T];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned int nent = *a.left_count;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  const int k1 = a.k + 1;
+  unsigned long long npairs = 0;
+  for (unsigned int e = blockIdx.x; e < nent; e += gridDim.x) {
+    const LeftEntry le = a.left_list[e];
+    double q[D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) q[t] = a.P[a.rows.row[t] * a.stride + le.slot];
+    double best[K1T];
+#pragma unroll
+    for (int t = 0; t < K1T; ++t) best[t] = kInf;
+    const double gate = a.left_best[(int64_t)le.slot * K1T + (K1T - 1)];   // current k-th distance (upper bound of eps)
+    double thr = gate;
+    const double* srow = a.P + a.sort_row * a.stride + le.c_lo;
+    const double q0 = q[0];
+    // candidates that can still enter: gap in the sorted coordinate below the gate (monotone => exact)
+    int lo = le.rstart, hi = le.rstart;
+    if (le.rstart < le.c_len) hi = warp_first_true(le.rstart, le.c_len, [&](int s) { return (srow[s] - q0) >= gate; });
+    int lo2 = le.lend, hi2 = le.lend;
+    if (le.lend > 0) lo2 = warp_first_true(0, le.lend, [&](int s) { return !((q0 - srow[s]) >= gate); });
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int b = pass == 0 ? lo : lo2, en = pass == 0 ? hi : hi2;
+      for (int base = b; base < en; base += kThreads * U) {
+        double c[U][D];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = min(base + u * kThreads + tid, en - 1);
+#pragma unroll
+          for (int t = 0; t < D; ++t) c[u][t] = a.P[a.rows.row[t] * a.stride + le.c_lo + j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (base + u * kThreads + tid < en) {
+            const double m = cheb<D>(q, c[u]);
+            if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
+          }
+        }
+      }
+      if (tid == 0) npairs += (unsigned long long)(en - b);
+    }
+    // per-warp merge -> shared; then warp 0 merges the NW warp lists and the stored list
+    const double mine = warp_merge_lists<K1T>(best, K1T);
+    if (lane < K1T) wlist[warp][lane] = mine;
+    if (warp == 0 && lane < K1T) wlist[NW][lane] = a.left_best[(int64_t)le.slot * K1T + lane];
+    __syncthreads();
+    if (warp == 0) {
+      double l2[K1T];
+#pragma unroll
+      for (int t = 0; t < K1T; ++t) l2[t] = (lane <= NW) ? wlist[lane][t] : kInf;
+      const double fin = warp_merge_lists<K1T>(l2, k1);
+      if (lane == a.k) a.eps[le.slot] = fin;
+    }
+    __syncthreads();
+  }
+  if (a.pairs && tid == 0 && npairs) atomicAdd(a.pairs, npairs);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -306,10 +566,12 @@ template <int C, int E>
 __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(const CountArgs a) {
   constexpr int D = C + E;
   constexpr int TC = chunk_len(D);
+  constexpr int CS = (C > 0 ? C : 1), ES = (E > 0 ? E : 1);
   __shared__ __align__(128) double sbuf[D * TC];
+  __shared__ __align__(16) double xch[kTileQ];
+  __shared__ int sidx[kTileQ];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ double red[kThreads / 32 + 1];
-  __shared__ int range[2];
+  __shared__ int wrange[2 * (kThreads / 32)];
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -319,6 +581,7 @@ __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(c
   __syncthreads();
   uint32_t phase = 0;
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   RowSel brows;
 #pragma unroll
   for (int t = 0; t < C; ++t) brows.row[t] = a.b_srow.row[t];
@@ -327,14 +590,16 @@ __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(c
 
   for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = a.tiles[tile_id];
-    double qs[kQpt][C > 0 ? C : 1];
-    double qe[kQpt][E > 0 ? E : 1];
+    double qs[kQpt][CS];
+    double qe[kQpt][ES];
     double r[kQpt];
     int ns[kQpt], ne0[kQpt], ne1[kQpt];
+    int qslot[kQpt];
     bool valid[kQpt];
 #pragma unroll
     for (int i = 0; i < kQpt; ++i) {
       const int qi = tid + i * kThreads;
+      qslot[i] = qi;
       valid[i] = qi < tile.q_n;
       const int slot = tile.q_lo + qi;
 #pragma unroll
@@ -346,40 +611,89 @@ __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(c
     }
 
     const int len_pad = (tile.c_len + kSegAlign - 1) / kSegAlign * kSegAlign;
-    int ch_lo = 0, ch_hi = (len_pad + TC - 1) / TC;   // chunk range [ch_lo, ch_hi)
+    int ch_lo = 0, ch_hi = (len_pad + TC - 1) / TC;   // chunk range [ch_lo, ch_hi) of the CTA
+    int w_lo = ch_lo, w_hi = ch_hi;                   // ... and of this warp
     if (a.prune_b_row >= 0) {
-      // candidates outside [min(q) - max(r), max(q) + max(r)] in the sorted coordinate cannot be
-      // neighbours of any query of this tile; the bounds are widened by 2^-50 relative so that
-      // the rounded subtraction in the exact test can never disagree with them.
-      double vmin = __longlong_as_double(0x7ff0000000000000LL), vmax = -vmin, rmax = -vmin;
+      // the pruning coordinate is the first shared one (or the only extra one): host guarantees it
+      // 1. regroup the tile's queries by radius so that warps are homogeneous
+#pragma unroll
+      for (int i = 0; i < kQpt; ++i) {
+        xch[tid + i * kThreads] = valid[i] ? r[i] : -kInf;
+        sidx[tid + i * kThreads] = tid + i * kThreads;
+      }
+      __syncthreads();
+      cta_sort_keys(xch, sidx);
+      int src[kQpt];
+#pragma unroll
+      for (int i = 0; i < kQpt; ++i) src[i] = sidx[kQpt * tid + i];
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < C; ++t) {
+        double v[kQpt];
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) v[i] = qs[i][t];
+        cta_permute(xch, src, v);
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) qs[i][t] = v[i];
+      }
+#pragma unroll
+      for (int t = 0; t < E; ++t) {
+        double v[kQpt];
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) v[i] = qe[i][t];
+        cta_permute(xch, src, v);
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) qe[i][t] = v[i];
+      }
+      cta_permute(xch, src, r);
+#pragma unroll
+      for (int i = 0; i < kQpt; ++i) {
+        qslot[i] = src[i];
+        valid[i] = src[i] < tile.q_n;
+      }
+      // 2. per warp: candidates outside [min(q) - max(r), max(q) + max(r)] in the sorted coordinate cannot
+      //    be neighbours of any of its queries; the bounds are widened by 2^-50 relative so that the
+      //    rounded subtraction in the exact test can never disagree with them.
+      double vmin = kInf, vmax = -kInf, rmax = -kInf;
 #pragma unroll
       for (int i = 0; i < kQpt; ++i) {
         if (valid[i]) {
-          const double v = a.Q[a.prune_q_row * a.qstride + tile.q_lo + tid + i * kThreads];
+          const double v = (C > 0) ? qs[i][0] : qe[i][0];
           vmin = fmin(vmin, v);
           vmax = fmax(vmax, v);
           rmax = fmax(rmax, r[i]);
         }
       }
-      vmin = block_min_bcast<kThreads>(vmin, red);
-      vmax = block_max_bcast<kThreads>(vmax, red);
-      rmax = block_max_bcast<kThreads>(rmax, red);
-      if (tid == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      }
+      int s_lo = 0, s_hi = 0;
+      if ((tid & 31) == 0 && rmax >= 0.0) {    // rmax < 0: every radius negative (or no query), nothing to count
         const double slack = 8.881784197001252e-16;  // 2^-50
         const double lo_v = (vmin - rmax) - (fabs(vmin) + fabs(rmax)) * slack;
         const double hi_v = (vmax + rmax) + (fabs(vmax) + fabs(rmax)) * slack;
         const double* col = a.B + a.prune_b_row * a.bstride + tile.c_lo;
-        int s_lo = 0, s_hi = 0;
-        if (rmax >= 0.0) {   // rmax < 0: every radius negative, nothing can be counted
-          s_lo = lower_bound_ge(col, tile.c_len, lo_v);
-          s_hi = upper_bound_gt(col, tile.c_len, hi_v);
-        }
-        range[0] = s_lo / TC;
-        range[1] = s_hi > s_lo ? (s_hi + TC - 1) / TC : s_lo / TC;
+        s_lo = lower_bound_ge(col, tile.c_len, lo_v);
+        s_hi = upper_bound_gt(col, tile.c_len, hi_v);
+      }
+      s_lo = __shfl_sync(0xffffffffu, s_lo, 0);
+      s_hi = __shfl_sync(0xffffffffu, s_hi, 0);
+      w_lo = s_lo / TC;
+      w_hi = s_hi > s_lo ? (s_hi + TC - 1) / TC : w_lo;
+      if ((tid & 31) == 0) {
+        wrange[2 * (tid >> 5)] = w_hi > w_lo ? w_lo : 0x7fffffff;
+        wrange[2 * (tid >> 5) + 1] = w_hi > w_lo ? w_hi : 0;
       }
       __syncthreads();
-      ch_lo = range[0];
-      ch_hi = range[1];
+      ch_lo = 0x7fffffff; ch_hi = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) {
+        ch_lo = min(ch_lo, wrange[2 * w]);
+        ch_hi = max(ch_hi, wrange[2 * w + 1]);
+      }
       __syncthreads();
     }
     unsigned long long npairs = 0;
@@ -390,35 +704,55 @@ __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(c
       if (tid == 0) stage_chunk<D, TC>(sbuf, &bar, a.B, a.bstride, brows, tile.c_lo + c_off, len);
       mbar_wait(&bar, phase);
       phase ^= 1;
-      npairs += (unsigned long long)min(TC, tile.c_len - c_off);
-
-#pragma unroll 2
-      for (int jj = 0; jj < len; jj += 2) {
-        double c0[D], c1[D];
+      if (j >= w_lo && j < w_hi) {
+        if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - c_off) * 32 * kQpt;
+#pragma unroll 1
+        for (int jj = 0; jj < len; jj += kGroup) {
+          double c[kGroup][D];
 #pragma unroll
-        for (int t = 0; t < D; ++t) {
-          const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj]);
-          c0[t] = v.x;
-          c1[t] = v.y;
-        }
+          for (int t = 0; t < D; ++t) {
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) {
-          if constexpr (C > 0) {
-            bool h0 = fabs(qs[i][0] - c0[0]) <= r[i];
-            bool h1 = fabs(qs[i][0] - c1[0]) <= r[i];
-#pragma unroll
-            for (int t = 1; t < C; ++t) {
-              h0 = h0 && (fabs(qs[i][t] - c0[t]) <= r[i]);
-              h1 = h1 && (fabs(qs[i][t] - c1[t]) <= r[i]);
+            for (int u = 0; u < kGroup; u += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj + u]);
+              c[u][t] = v.x;
+              c[u + 1][t] = v.y;
             }
-            if (h0 | h1) {
-              ns[i] += (int)h0 + (int)h1;
-              if constexpr (E > 0) ne0[i] += (int)(h0 && fabs(qe[i][0] - c0[C]) <= r[i]) + (int)(h1 && fabs(qe[i][0] - c1[C]) <= r[i]);
-              if constexpr (E > 1) ne1[i] += (int)(h0 && fabs(qe[i][1] - c0[C + 1]) <= r[i]) + (int)(h1 && fabs(qe[i][1] - c1[C + 1]) <= r[i]);
+          }
+          if constexpr (C > 0) {
+            // the shared coordinates decide; the private ones are only looked at for pairs that pass
+            bool h[kQpt][kGroup];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i) {
+#pragma unroll
+              for (int u = 0; u < kGroup; ++u) {
+                bool in = fabs(qs[i][0] - c[u][0]) <= r[i];
+#pragma unroll
+                for (int t = 1; t < C; ++t) in = in && (fabs(qs[i][t] - c[u][t]) <= r[i]);
+                h[i][u] = in;
+                any = any | in;
+              }
+            }
+            if (any) {
+#pragma unroll
+              for (int i = 0; i < kQpt; ++i) {
+#pragma unroll
+                for (int u = 0; u < kGroup; ++u) {
+                  ns[i] += (int)h[i][u];
+                  if constexpr (E > 0) ne0[i] += (int)(h[i][u] && fabs(qe[i][0] - c[u][C]) <= r[i]);
+                  if constexpr (E > 1) ne1[i] += (int)(h[i][u] && fabs(qe[i][1] - c[u][C + 1]) <= r[i]);
+                }
+              }
             }
           } else {
-            if constexpr (E > 0) ne0[i] += (int)(fabs(qe[i][0] - c0[0]) <= r[i]) + (int)(fabs(qe[i][0] - c1[0]) <= r[i]);
-            if constexpr (E > 1) ne1[i] += (int)(fabs(qe[i][1] - c0[1]) <= r[i]) + (int)(fabs(qe[i][1] - c1[1]) <= r[i]);
+#pragma unroll
+            for (int i = 0; i < kQpt; ++i) {
+#pragma unroll
+              for (int u = 0; u < kGroup; ++u) {
+                if constexpr (E > 0) ne0[i] += (int)(fabs(qe[i][0] - c[u][0]) <= r[i]);
+                if constexpr (E > 1) ne1[i] += (int)(fabs(qe[i][1] - c[u][1]) <= r[i]);
+              }
+            }
           }
         }
       }
@@ -428,13 +762,17 @@ __global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(c
 #pragma unroll
     for (int i = 0; i < kQpt; ++i) {
       if (valid[i]) {
-        const int slot = tile.q_lo + tid + i * kThreads;
+        const int slot = tile.q_lo + qslot[i];
         if constexpr (C > 0) a.cnt_s[slot] = ns[i];
         if constexpr (E > 0) a.cnt_e0[slot] = ne0[i];
         if constexpr (E > 1) a.cnt_e1[slot] = ne1[i];
       }
     }
-    if (tid == 0 && a.pairs) atomicAdd(a.pairs, npairs * (unsigned long long)tile.q_n);
+    if (a.pairs) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+      if ((tid & 31) == 0 && npairs) atomicAdd(a.pairs, npairs);
+    }
   }
 }
 

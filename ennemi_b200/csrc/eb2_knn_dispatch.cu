@@ -18,6 +18,33 @@ static cudaError_t launch_d(const KnnArgs& a, int grid, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <int D>
+static cudaError_t launch_left_d(const KnnArgs& a, int grid, cudaStream_t s) {
+  const int k1 = a.k + 1;
+  if (k1 <= 4) knn_leftover_kernel<D, 4><<<grid, kThreads, 0, s>>>(a);
+  else if (k1 <= 8) knn_leftover_kernel<D, 8><<<grid, kThreads, 0, s>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_leftover(int D, const KnnArgs& a, int grid, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_left_d<1>(a, grid, s);
+    case 2: return launch_left_d<2>(a, grid, s);
+    case 3: return launch_left_d<3>(a, grid, s);
+    case 4: return launch_left_d<4>(a, grid, s);
+    case 5: return launch_left_d<5>(a, grid, s);
+    case 6: return launch_left_d<6>(a, grid, s);
+    case 7: return launch_left_d<7>(a, grid, s);
+    case 8: return launch_left_d<8>(a, grid, s);
+    case 9: return launch_left_d<9>(a, grid, s);
+    case 10: return launch_left_d<10>(a, grid, s);
+    case 11: return launch_left_d<11>(a, grid, s);
+    case 12: return launch_left_d<12>(a, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launch_knn(int D, const KnnArgs& a, int grid, cudaStream_t s) {
   switch (D) {
     case 1: return launch_d<1>(a, grid, s);

@@ -8,6 +8,8 @@ namespace eb2 {
 // larger k the heap variant (args.heap must then hold (k+1) * grid * kTileQ doubles).
 cudaError_t launch_knn(int D, const KnnArgs& args, int grid, cudaStream_t stream);
 int knn_grid(int k, int ntiles, int sm_count);
+// finishes the queries knn_kernel deferred (register top-k variants only)
+cudaError_t launch_knn_leftover(int D, const KnnArgs& args, int grid, cudaStream_t stream);
 // C shared + E private coordinates
 cudaError_t launch_count(int C, int E, const CountArgs& args, int grid, cudaStream_t stream);
 }  // namespace eb2

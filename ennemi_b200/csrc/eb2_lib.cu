@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -274,6 +275,17 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
       rank += qn;
     }
   }
+  if (ps.sort_row >= 0 && t.size() > 2) {
+    // tiles at the two ends of the sorted coordinate sit in sparse regions and search the widest
+    // windows: launch them first (CTAs are dispatched in table order) so they do not form the tail
+    std::vector<Tile> o;
+    o.reserve(t.size());
+    for (size_t a = 0, b = t.size() - 1; a <= b && b < t.size(); ++a, --b) {
+      o.push_back(t[a]);
+      if (b != a) o.push_back(t[b]);
+    }
+    t.swap(o);
+  }
   TileSet ts;
   ts.count = static_cast<int>(t.size());
   ts.rows = rows;
@@ -297,11 +309,32 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
   if (!ts.count) return;
   KnnArgs a;
   a.P = ps.P; a.stride = ps.stride; a.rows = rows; a.tiles = ts.dev; a.k = k;
-  a.sort_row = ps.sort_row; a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
+  a.sort_row = -1;
+  // pruning needs the sorted coordinate to be a coordinate of the search space; the kernel reads it
+  // as the query's coordinate 0 (the order of coordinates is irrelevant to the max-norm)
+  for (int t = 0; t < D && ps.sort_row >= 0; ++t)
+    if (rows.row[t] == ps.sort_row) { std::swap(a.rows.row[0], a.rows.row[t]); a.sort_row = ps.sort_row; break; } a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
+  a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
+  const int k1t = (k + 1 <= 4) ? 4 : 8;
+  if (a.sort_row >= 0 && k + 1 <= 8) {
+    a.defer_below = 16;
+    if (const char* e = getenv("EB2_DEFER")) a.defer_below = atoi(e);     // tuning knob
+  }
+  if (a.defer_below > 0) {
+    a.left_list = s.dev<LeftEntry>(ps.stride);
+    a.left_count = s.dev<unsigned int>(1);
+    a.left_best = s.dev<double>(static_cast<size_t>(ps.stride) * k1t);
+    CU(cudaMemsetAsync(a.left_count, 0, sizeof(unsigned int), s.c.stream));
+  }
   const int grid = knn_grid(k, ts.count, s.c.sm_count);
   if (k + 1 > 8) a.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * kTileQ);
   CU(launch_knn(D, a, grid, s.c.stream));
   s.launches++;
+  if (a.defer_below > 0) {
+    // entry count stays on the device: a fixed persistent grid walks the list
+    CU(launch_knn_leftover(D, a, s.c.sm_count * 8, s.c.stream));
+    s.launches++;
+  }
 }
 
 struct CountOut {
@@ -321,9 +354,15 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
   a.radius = radius; a.tiles = ts.dev; a.ntiles = ts.count;
   a.prune_q_row = -1; a.prune_b_row = -1;
   if (prune && bs.sort_row >= 0) {
-    // the sorted coordinate of the candidate set must be one of the coordinates of the marginal
+    // the sorted coordinate of the candidate set must be a SHARED coordinate of the marginals (or the
+    // only coordinate); the kernel reads it as the query's shared coordinate 0
     for (int t = 0; t < C; ++t)
-      if (b_srow.row[t] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_srow.row[t]; }
+      if (b_srow.row[t] == bs.sort_row) {
+        std::swap(a.b_srow.row[0], a.b_srow.row[t]);
+        std::swap(a.q_srow.row[0], a.q_srow.row[t]);
+        a.prune_b_row = bs.sort_row; a.prune_q_row = a.q_srow.row[0];
+        break;
+      }
     if (C == 0 && E == 1 && b_erow.row[0] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_erow.row[0]; }
   }
   a.cnt_s = out.s; a.cnt_e0 = out.e0; a.cnt_e1 = out.e1; a.pairs = pairs;
