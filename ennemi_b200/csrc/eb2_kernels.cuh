@@ -164,12 +164,66 @@ __device__ __forceinline__ void cta_permute(double* xch, const int (&src)[kQpt],
   __syncthreads();
 }
 
-constexpr int kGroup = 4;   // candidates tested per branch in the all-pairs inner loops
+// candidates tested per branch in the all-pairs inner loops (register budget: 2*G*D for the group)
+__host__ __device__ constexpr int group_len(int d) { return d <= 2 ? 4 : 2; }
+// resident CTAs per SM the kernels are compiled for, from a register estimate:
+// queries 4*D + lists 4*K1T + candidate group 2*G*D + ~34 bookkeeping
+__host__ __device__ constexpr int knn_min_blocks(int d, int k1t) {
+  const int regs = 4 * d + 4 * k1t + 2 * group_len(d) * d + 40;
+  return regs <= 80 ? 3 : (regs <= 128 ? 2 : 1);
+}
+
+// all queries of one thread against one staged candidate chunk (shared memory, broadcast LDS.128)
+template <int D, int K1T, int TC>
+__device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, const double (&q)[kQpt][D],
+                                               double (&best)[kQpt][(K1T > 0 ? K1T : 1)], double (&thr)[kQpt],
+                                               const HeapRef (&heap)[kQpt]) {
+  constexpr int kGroup = group_len(D);
+#pragma unroll 1
+  for (int jj = 0; jj < len; jj += kGroup) {
+    bool any = false;
+    {
+      double c[kGroup][D];
+#pragma unroll
+      for (int t = 0; t < D; ++t) {
+#pragma unroll
+        for (int u = 0; u < kGroup; u += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj + u]);
+          c[u][t] = v.x;
+          c[u + 1][t] = v.y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kQpt; ++i) {
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) any = any | inside_lt<D>(q[i], c[u], thr[i]);
+      }
+    }
+    if (any) {   // some lane has a new neighbour: re-test pair by pair (the k-th distance moves);
+                 // candidates are re-read from shared memory so the group need not stay in registers
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        double cu[D];
+#pragma unroll
+        for (int t = 0; t < D; ++t) cu[t] = sbuf[t * TC + jj + u];
+#pragma unroll
+        for (int i = 0; i < kQpt; ++i) {
+          if (inside_lt<D>(q[i], cu, thr[i])) {
+            const double m = cheb<D>(q[i], cu);
+            if constexpr (K1T > 0) { topk_insert<K1T>(best[i], m); thr[i] = best[i][K1T - 1]; }
+            else thr[i] = heap[i].replace_root(m);
+          }
+        }
+      }
+    }
+  }
+}
 
 // K1T > 0: register-resident sorted top-K1T (k+1 <= K1T).  K1T == 0: heap in global scratch, any k.
 template <int D, int K1T>
-__global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const KnnArgs a) {
+__global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(const KnnArgs a) {
   constexpr int TC = chunk_len(D);
+  constexpr int kGroup = group_len(D);
   constexpr int NB = (K1T > 0 ? K1T : 1);
   __shared__ __align__(128) double sbuf[D * TC];
   __shared__ __align__(16) double xch[kTileQ];
@@ -222,41 +276,6 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
     const bool prune = a.sort_row >= 0;      // then rows.row[0] == sort_row (host guarantees it)
     unsigned long long npairs = 0;
 
-    // all queries of this thread against one staged chunk
-    auto scan_chunk = [&](int len) {
-#pragma unroll 1
-      for (int jj = 0; jj < len; jj += kGroup) {
-        double c[kGroup][D];
-#pragma unroll
-        for (int t = 0; t < D; ++t) {
-#pragma unroll
-          for (int u = 0; u < kGroup; u += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(&sbuf[t * TC + jj + u]);
-            c[u][t] = v.x;
-            c[u + 1][t] = v.y;
-          }
-        }
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < kQpt; ++i) {
-#pragma unroll
-          for (int u = 0; u < kGroup; ++u) any = any | inside_lt<D>(q[i], c[u], thr[i]);
-        }
-        if (any) {   // some lane has a new neighbour: re-test pair by pair (the k-th distance moves)
-#pragma unroll
-          for (int u = 0; u < kGroup; ++u) {
-#pragma unroll
-            for (int i = 0; i < kQpt; ++i) {
-              if (inside_lt<D>(q[i], c[u], thr[i])) {
-                const double m = cheb<D>(q[i], c[u]);
-                if constexpr (K1T > 0) { topk_insert<K1T>(best[i], m); thr[i] = best[i][K1T - 1]; }
-                else thr[i] = heap[i].replace_root(m);
-              }
-            }
-          }
-        }
-      }
-    };
     auto fetch_chunk = [&](int j) -> int {
       const int c_off = j * TC;
       const int len = min(TC, len_pad - c_off);
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
       for (int j = 0; j < nchunks; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        scan_chunk(len);
+        knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
         __syncthreads();   // everyone is done with sbuf before the next bulk copy lands in it
       }
     } else {
@@ -280,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
       for (int j = home_lo; j <= home_hi; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        scan_chunk(len);
+        knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
         __syncthreads();
       }
       if (home_lo > 0 || home_hi + 1 < nchunks) {
@@ -348,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
           const int len = fetch_chunk(j);
           if (wneed) {
             if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
-            scan_chunk(len);
+            knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -369,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, (D <= 4 ? 3 : 2)) knn_kernel(const K
           const int len = fetch_chunk(j);
           if (wneed) {
             if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
-            scan_chunk(len);
+            knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -563,9 +582,10 @@ __device__ __forceinline__ int upper_bound_gt(const double* a, int len, double v
 }
 
 template <int C, int E>
-__global__ void __launch_bounds__(kThreads, (C + E <= 4 ? 3 : 2)) count_kernel(const CountArgs a) {
+__global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kernel(const CountArgs a) {
   constexpr int D = C + E;
   constexpr int TC = chunk_len(D);
+  constexpr int kGroup = group_len(D);
   constexpr int CS = (C > 0 ? C : 1), ES = (E > 0 ? E : 1);
   __shared__ __align__(128) double sbuf[D * TC];
   __shared__ __align__(16) double xch[kTileQ];
