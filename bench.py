@@ -39,6 +39,9 @@ K_NEIGH = 3
 RHO = 0.6
 FP64_OPS_PER_PAIR = 4          # 2-D space: 2 subtractions + 2 compares (2d per pair)
 SAMPLE_STRIDE = 20             # CPU baseline: every 20th row is queried, trees hold all rows
+# dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel<2,4> at this workload, one ncu --set full capture
+# (profiles/ncu_r01_summary.md): the 16 MB point set is read once, everything else stays in the 126 MB L2
+NCU_DRAM_BYTES_PER_LAUNCH = 16.4e6
 
 
 def make_data(n=N_ROWS):
@@ -226,6 +229,16 @@ def run_gpu(args):
     ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
 
+    # task fan-out (weak scaling): every rank estimates its own resident batch per step, no collective
+    fan = None
+    if world > 1:
+        def step_fanout():
+            nat.ksg_mi_rows(int(coords_dev.data_ptr()), N_ROWS, K_NEIGH, 0, N_ROWS, dev=local, flags=nat.FLAG_DEVICE_INPUT)
+            return None
+        ms_f, _, _, _ = timed_steps(step_fanout, args.steps, 1)
+        fan = {"value": world * 1e3 / (ms_f / args.steps), "unit": UNIT, "scaling": "weak", "ms_per_step": ms_f / args.steps,
+               "note": "independent (pair / lag) tasks fanned out: one full N=1e6 estimate per rank per step, no collective"}
+
     brute = None
     if world == 1 and not args.no_brute:
         bsteps = max(2, min(args.steps, 3))
@@ -258,13 +271,15 @@ def run_gpu(args):
                 "mi": last.get("e2e")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
                      "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
                              "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
                              "ops = pairs actually evaluated x 4"},
         "clocks": clocks,
     }
+    if fan:
+        line["fanout"] = fan
     if brute:
         b_ms, b_knn, b_pairs, b_val = brute
         b_ops = float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR

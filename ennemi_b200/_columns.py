@@ -1,0 +1,223 @@
+"""Device-resident columns for lag sweeps and ``pairwise_mi``.
+
+The reference prepares every (variable, lag) task from scratch on the host: slice, rescale, add
+noise, build trees.  Here every variable of a call is uploaded to the GPU ONCE; a task is then just
+a list of column descriptors — which cached column, the lag offset, the window length, the mean and
+standard deviation of that window (computed by NumPy on the host exactly as the reference does, so
+the bits agree) and which cached noise vector to add.  The rescaling arithmetic itself runs on the
+device (``prep_kernel``), bit-identically to ``ennemi/_driver.py:882-883``.
+
+Eligible tasks: continuous float64 variables, no mask, and no NaN dropping (``drop_nan`` with data
+that has no NaNs is a no-op and stays eligible).  Everything else takes the general host path.
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _align, _checks, _devices, _native
+
+_next_key = itertools.count(1)
+_key_lock = threading.Lock()
+
+
+def _new_key() -> int:
+    with _key_lock:
+        return next(_next_key)
+
+
+class _Scratch(threading.local):
+    buf: Optional[np.ndarray] = None
+
+
+_scratch = _Scratch()
+
+
+def window_stats(view: np.ndarray) -> Tuple[float, float]:
+    """``(view.mean(), view.std())`` with NumPy's own operation sequence (``_methods._mean`` /
+    ``_methods._var``: pairwise ``add.reduce``, subtract, multiply, ``add.reduce``, sqrt), hence the
+    same bits, but into a reused per-thread scratch buffer instead of fresh temporaries."""
+    n = view.shape[0]
+    mean = np.add.reduce(view) / n
+    buf = _scratch.buf
+    if buf is None or buf.shape[0] < n:
+        buf = _scratch.buf = np.empty(max(n, 1 << 16))
+    dev = buf[:n]
+    np.subtract(view, mean, out=dev)
+    np.multiply(dev, dev, out=dev)
+    std = np.sqrt(np.add.reduce(dev) / n)
+    return float(mean), float(std)
+
+
+class NoiseBank:
+    """The reference's fixed-seed noise draws (``_driver.py:874,883``), memoised on the host by
+    ``_align._NoiseStream`` and mirrored on each GPU under a cache key."""
+
+    _lock = threading.Lock()
+    _keys: "OrderedDict[tuple, int]" = OrderedDict()        # draw-shape sequence -> cache key
+    _on_device: Dict[int, set] = {}
+    MAX_ENTRIES = 64
+
+    @classmethod
+    def key_for(cls, shapes: tuple, values: np.ndarray, dev: int) -> int:
+        with cls._lock:
+            key = cls._keys.get(shapes)
+            if key is None:
+                key = _new_key()
+                cls._keys[shapes] = key
+                while len(cls._keys) > cls.MAX_ENTRIES:
+                    _, old = cls._keys.popitem(last=False)
+                    for d, have in cls._on_device.items():
+                        if old in have:
+                            have.discard(old)
+                            _native.cache_drop(old, dev=d)
+            else:
+                cls._keys.move_to_end(shapes)
+            have = cls._on_device.setdefault(dev, set())
+            if key not in have:
+                _native.cache_put(key, np.ravel(values), dev=dev)
+                have.add(key)
+            return key
+
+
+class ColumnStore:
+    """The variables of one API call, uploaded lazily to each GPU that runs one of its tasks."""
+
+    def __init__(self):
+        self._cols: Dict[int, np.ndarray] = {}
+        self._on_device: Dict[int, set] = {}
+        self._lock = threading.Lock()
+        self._stats: Dict[tuple, tuple] = {}
+
+    def add(self, column: np.ndarray) -> int:
+        key = _new_key()
+        self._cols[key] = np.ascontiguousarray(column, dtype=np.float64)
+        return key
+
+    def ensure(self, dev: int, key: int) -> None:
+        with self._lock:
+            have = self._on_device.setdefault(dev, set())
+            if key not in have:
+                _native.cache_put(key, self._cols[key], dev=dev)
+                have.add(key)
+
+    def stats(self, tag: tuple, compute):
+        with self._lock:
+            hit = self._stats.get(tag)
+        if hit is None:
+            hit = compute()
+            with self._lock:
+                self._stats[tag] = hit
+        return hit
+
+    def close(self) -> None:
+        for dev, have in self._on_device.items():
+            for key in have:
+                try:
+                    _native.cache_drop(key, dev=dev)
+                except Exception:
+                    pass
+        self._on_device.clear()
+        self._cols.clear()
+
+
+def eligible(arrays, mask, drop_nan: bool, discrete_any: bool) -> bool:
+    if discrete_any or mask is not None:
+        return False
+    for a in arrays:
+        if a is None:
+            continue
+        if a.dtype != np.float64:
+            return False
+    if drop_nan:
+        for a in arrays:
+            if a is not None and np.isnan(a).any():
+                return False
+    return True
+
+
+class ColsTask:
+    """A continuous (x, y[, cond]) task on cached columns; ``run()`` returns the estimate."""
+
+    __slots__ = ("store", "xkey", "ykey", "zkeys", "xview", "yview", "cond", "lag", "hi", "lo", "cond_lag", "k",
+                 "preprocess", "n_total")
+
+    def __init__(self, store, xkey, ykey, zkeys, xview, yview, cond, lag, hi, lo, cond_lag, k, preprocess):
+        self.store, self.xkey, self.ykey, self.zkeys = store, xkey, ykey, zkeys
+        self.xview, self.yview, self.cond = xview, yview, cond
+        self.lag, self.hi, self.lo, self.cond_lag, self.k, self.preprocess = lag, hi, lo, cond_lag, k, preprocess
+        self.n_total = len(yview)
+
+    def run(self) -> float:
+        dev = _devices.current()
+        lo_pad, hi_pad = max(self.hi, 0), min(self.lo, 0)            # as _align.lagged_windows
+        n_tot = self.n_total
+        xs = self.xview[lo_pad - self.lag: n_tot - self.lag + hi_pad]   # views: non-integer lags raise here
+        ys = self.yview[lo_pad: n_tot + hi_pad]
+        n = len(ys)
+        if n <= self.k:
+            raise ValueError(_checks.MSG_K_TOO_LARGE)
+        x_off = int(lo_pad - self.lag)
+        y_off = int(lo_pad)
+        z_offs = [int(lo_pad - cl) for cl in self.cond_lag] if self.zkeys else []
+
+        shapes: tuple = ()
+        stream = _align._NoiseStream()
+        descs: List[_native.ColDesc] = []
+
+        def one(key, off, view, tag):
+            nonlocal shapes
+            self.store.ensure(dev, key)
+            mean, std, nkey = 0.0, 0.0, 0
+            if self.preprocess:
+                mean, std = self.store.stats(tag, lambda: window_stats(view))
+                if abs(std) < _align.CONSTANT_STD:
+                    warnings.warn(_align.CONSTANT_DATA_WARNING)
+                    std = 0.0
+                elif std == std:                                    # NaN std (NaN input): reported by the device
+                    values = stream.normal((n,))
+                    shapes = shapes + ((n,),)
+                    nkey = NoiseBank.key_for(shapes, values, dev)
+                else:
+                    std = 0.0
+            return _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
+
+        descs.append(one(self.xkey, x_off, xs, (self.xkey, x_off, n)))
+        descs.append(one(self.ykey, y_off, ys, (self.ykey, y_off, n)))
+        if self.zkeys:
+            c = len(self.zkeys)
+            zstd = zmean = None
+            nkey = 0
+            if self.preprocess:
+                def zstats():
+                    zs = np.column_stack([self.cond[o: o + n, j] for j, o in enumerate(z_offs)])
+                    return zs.mean(axis=0), zs.std(axis=0)       # axis-0 reductions, exactly as :895-899
+                zmean, zstd = self.store.stats(("z", tuple(self.zkeys), tuple(z_offs), n), zstats)
+                if np.any(np.abs(zstd) < _align.CONSTANT_STD):
+                    warnings.warn(_align.CONSTANT_DATA_WARNING)
+                    zstd = None
+                elif not np.any(np.isnan(zstd)):
+                    values = stream.normal((n, c))
+                    shapes = shapes + ((n, c),)
+                    nkey = NoiseBank.key_for(shapes, values, dev)
+                else:
+                    zstd = None
+            for j, (key, off) in enumerate(zip(self.zkeys, z_offs)):
+                self.store.ensure(dev, key)
+                if zstd is None:
+                    descs.append(_native.ColDesc(key, off, 1, 0.0, 0.0, 0, 0, 1))
+                else:
+                    descs.append(_native.ColDesc(key, off, 1, float(zmean[j]), float(zstd[j]), nkey, j, c))
+        try:
+            if self.zkeys:
+                return _native.cmi_cols(descs, n, self.k, dev=dev)
+            return _native.ksg_mi_cols(descs, n, self.k, dev=dev)
+        except _native.NonFiniteInput as e:
+            if e.nan:
+                raise ValueError(_checks.MSG_NANS_LEFT) from None
+            raise ValueError(str(e)) from None

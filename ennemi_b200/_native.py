@@ -31,10 +31,19 @@ EXPORTS = (
     "eb2_ross_mi", "eb2_ross_cmi",
     "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
+    "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
 )
 
 _lib = None
 _lib_lock = threading.Lock()
+
+
+class ColDesc(ctypes.Structure):
+    """``eb2_col_t``: one coordinate of the joint space taken from the device column cache."""
+    _fields_ = [("key", ctypes.c_uint64), ("off", ctypes.c_int64), ("stride", ctypes.c_int64),
+                ("mean", ctypes.c_double), ("std", ctypes.c_double),
+                ("nkey", ctypes.c_uint64), ("noff", ctypes.c_int64), ("nstride", ctypes.c_int64)]
+
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_lp = ctypes.POINTER(ctypes.c_int64)
@@ -76,6 +85,10 @@ def load():
         lib.eb2_ball_count.argtypes = [_int, _vp, _vp, _i64, _int, _int, _int, _vp, _u32, _vp]
         lib.eb2_last_timing.argtypes = [_int, _c_dp, ctypes.POINTER(_int)]
         lib.eb2_measure_fp64_peak.argtypes = [_int, _c_dp]
+        lib.eb2_cache_put.argtypes = [_int, ctypes.c_uint64, _vp, _i64]
+        lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
+        lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
+        lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
         for name in EXPORTS:
             getattr(lib, name)
         _lib = lib
@@ -301,3 +314,48 @@ def measure_fp64_peak(dev: int = 0) -> float:
     if rc:
         _raise(rc)
     return out.value
+
+
+class NonFiniteInput(ValueError):
+    """Raised by the ``*_cols`` calls; ``nan`` tells NaN input from otherwise non-finite data."""
+
+    def __init__(self, msg, nan):
+        super().__init__(msg)
+        self.nan = nan
+
+
+def cache_put(key: int, column: np.ndarray, dev: int = 0) -> None:
+    lib = load()
+    column = np.ascontiguousarray(column, dtype=np.float64)
+    rc = lib.eb2_cache_put(dev, key, column.ctypes.data, column.size)
+    if rc:
+        _raise(rc)
+
+
+def cache_drop(key: int, dev: int = 0) -> None:
+    lib = load()
+    rc = lib.eb2_cache_drop(dev, key)
+    if rc:
+        _raise(rc)
+
+
+def _cols_call(fn, cols, *args):
+    arr = (ColDesc * len(cols))(*cols)
+    value = ctypes.c_double()
+    rc = fn(*args[:1], arr, *args[1:], ctypes.byref(value))
+    if rc == ERR_NONFINITE:
+        lib = load()
+        raise NonFiniteInput(lib.eb2_last_error().decode(), bool(lib.eb2_last_data_flags() & 1))
+    if rc:
+        _raise(rc)
+    return value.value
+
+
+def ksg_mi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
+    """KSG MI of two cached device columns (``cols``: two :class:`ColDesc`)."""
+    return _cols_call(load().eb2_ksg_mi_cols, cols, dev, n, k, flags)
+
+
+def cmi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
+    """Frenzel-Pompe CMI of cached device columns (``cols``: x, y, then the condition's columns)."""
+    return _cols_call(load().eb2_cmi_cols, cols, dev, n, len(cols) - 2, k, flags)

@@ -9,14 +9,16 @@ GPUs of the box instead of a CPU thread pool.
 from __future__ import annotations
 
 import itertools
+import os
 import sys
 import warnings
 from typing import Callable, Optional
 
 import numpy as np
 
-from . import _align, _checks, _estimators as est, _schedule
+from . import _align, _checks, _columns, _estimators as est, _schedule
 from ._align import MiTask
+from ._columns import ColsTask
 
 DISCRETE_NORMALIZATION_WARNING = (
     "You have set normalize=True while at least one variable is discrete. "
@@ -127,9 +129,25 @@ def _entropy_of(x: np.ndarray, k: int, multidim: bool, mask, discrete: bool, dro
 # ---------------------------------------------------------------------------------------------
 # mutual information
 # ---------------------------------------------------------------------------------------------
-def _run_task(t: MiTask) -> float:
+# below this many rows the per-task host preparation is cheaper than caching columns on the device
+DEVICE_COLUMNS_MIN_ROWS = int(os.environ.get("ENNEMI_B200_COLUMNS_MIN_ROWS", "20000"))
+
+
+def _device_store(arrays, mask, drop_nan: bool, any_discrete: bool):
+    """A :class:`_columns.ColumnStore` when the call qualifies for device-resident columns, else None."""
+    from . import distributed
+    if arrays[0].shape[0] < DEVICE_COLUMNS_MIN_ROWS or distributed.row_sharding_enabled():
+        return None
+    if not _columns.eligible(arrays, mask, drop_nan, any_discrete):
+        return None
+    return _columns.ColumnStore()
+
+
+def _run_task(t) -> float:
     """Prepare one task on the host and dispatch to the estimator its variable types call for
     (``_driver.py:815-832``).  For a discrete variable the continuous one goes first."""
+    if isinstance(t, ColsTask):          # continuous variables already resident on the GPU
+        return t.run()
     xs, ys, zs = _align.prepare(t)
     if zs is None:
         if t.discrete_x and t.discrete_y:
@@ -185,8 +203,18 @@ def estimate_mi(y, x, lag=0, *, k: int = 3, cond=None, cond_lag=0, mask=None,
 
     n_var = 1 if x_arr.ndim == 1 else x_arr.shape[1]
     cells = list(itertools.product(range(len(lags)), range(n_var)))
-    tasks = [MiTask(x_arr if x_arr.ndim == 1 else x_arr[:, v], y_arr, lags[li], hi, lo, k, mask_arr, cond_arr,
-                    cond_lags[li], discrete_x, discrete_y, preprocess, drop_nan) for li, v in cells]
+    x_cols = [x_arr if x_arr.ndim == 1 else x_arr[:, v] for v in range(n_var)]
+    store = _device_store([x_arr, y_arr, cond_arr], mask_arr, drop_nan, discrete_x or discrete_y)
+    if store is not None:
+        # every variable goes to the GPU once; a task is a set of lag offsets into the cached columns
+        xkeys = [store.add(c) for c in x_cols]
+        ykey = store.add(y_arr)
+        zkeys = [] if cond_arr is None else [store.add(cond_arr[:, j]) for j in range(n_cond)]
+        tasks = [ColsTask(store, xkeys[v], ykey, zkeys, x_cols[v], y_arr, cond_arr, lags[li], hi, lo, cond_lags[li],
+                          k, preprocess) for li, v in cells]
+    else:
+        tasks = [MiTask(x_cols[v], y_arr, lags[li], hi, lo, k, mask_arr, cond_arr,
+                        cond_lags[li], discrete_x, discrete_y, preprocess, drop_nan) for li, v in cells]
 
     def done(i: int) -> None:
         if callback is not None:
@@ -194,7 +222,11 @@ def estimate_mi(y, x, lag=0, *, k: int = 3, cond=None, cond_lag=0, mask=None,
             callback(v, lags[li])
 
     per_task = _schedule.gpu_time_estimate(len(y_arr), 0 if cond_arr is None else n_cond, k)
-    values = _schedule.run_tasks(_run_task, tasks, max_threads, per_task, done)
+    try:
+        values = _schedule.run_tasks(_run_task, tasks, max_threads, per_task, done)
+    finally:
+        if store is not None:
+            store.close()
 
     result = np.empty((len(lags), n_var))
     for cell, value in zip(cells, values):
@@ -248,15 +280,26 @@ def pairwise_mi(data, *, k: int = 3, cond=None, mask=None, discrete=False, prepr
     n_obs, n_var = data_arr.shape
     zero_lag = np.asarray(0) if cond_arr is None else np.full(cond_arr.shape[1], 0)
     pairs = [(i, j) for i in range(n_var) for j in range(i + 1, n_var)]
-    tasks = [MiTask(data_arr[:, i], data_arr[:, j], 0, 0, 0, k, mask_arr, cond_arr, zero_lag,
-                    flags[i], flags[j], preprocess, drop_nan) for i, j in pairs]
+    store = _device_store([data_arr, cond_arr], mask_arr, drop_nan, bool(flags.any()))
+    if store is not None:
+        keys = [store.add(data_arr[:, v]) for v in range(n_var)]
+        zkeys = [] if cond_arr is None else [store.add(cond_arr[:, j]) for j in range(cond_arr.shape[1])]
+        tasks = [ColsTask(store, keys[i], keys[j], zkeys, data_arr[:, i], data_arr[:, j], cond_arr, 0, 0, 0,
+                          np.atleast_1d(zero_lag), k, preprocess) for i, j in pairs]
+    else:
+        tasks = [MiTask(data_arr[:, i], data_arr[:, j], 0, 0, 0, k, mask_arr, cond_arr, zero_lag,
+                        flags[i], flags[j], preprocess, drop_nan) for i, j in pairs]
 
     def done(t: int) -> None:
         if callback is not None:
             callback(*pairs[t])
 
     per_task = _schedule.gpu_time_estimate(n_obs, 0 if cond_arr is None else cond_arr.shape[1], k)
-    values = _schedule.run_tasks(_run_task, tasks, max_threads, per_task, done)
+    try:
+        values = _schedule.run_tasks(_run_task, tasks, max_threads, per_task, done)
+    finally:
+        if store is not None:
+            store.close()
 
     result = np.full((n_var, n_var), np.nan)
     for (i, j), value in zip(pairs, values):

@@ -187,10 +187,43 @@ __global__ void nonfinite_kernel(const double* v, int64_t count, int* flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) {
     const double x = v[i];
-    if (!(fabs(x) < __longlong_as_double(0x7ff0000000000000LL))) *flag = 1;
+    if (!(fabs(x) < __longlong_as_double(0x7ff0000000000000LL))) atomicOr(flag, 2);
   }
 }
 
+
+// cached columns -> the d x n block the estimators work on.  Rescaling is the reference's
+// (xs - xs.mean()) / std ; xs += noise  (ennemi/_driver.py:882-883): three correctly rounded fp64
+// operations in that order, nothing fused, so the block is bit-identical to the host-prepared one.
+struct PrepCol {
+  const double* src;
+  long long off, stride;
+  double mean, std;        // std == 0: pass the values through unchanged (no rescaling, no noise)
+  const double* noise;     // NULL: no noise
+  long long noff, nstride;
+};
+struct PrepArgs {
+  PrepCol col[kMaxDim];
+  int d;
+  long long n;
+  double* raw;
+  int* flags;              // bit0: NaN among the input values
+};
+
+__global__ void prep_kernel(const PrepArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n * a.d) return;
+  const int t = (int)(idx / a.n);
+  const long long i = idx - (long long)t * a.n;
+  const PrepCol& c = a.col[t];
+  double v = c.src[c.off + i * c.stride];
+  if (v != v) atomicOr(a.flags, 1);
+  if (c.std != 0.0) {
+    v = __ddiv_rn(__dsub_rn(v, c.mean), c.std);
+    if (c.noise) v = __dadd_rn(v, c.noise[c.noff + i * c.nstride]);
+  }
+  a.raw[idx] = v;
+}
 
 // register-resident DADD chains: the FP64 issue rate that bounds the all-pairs kernels
 __global__ void fp64_peak_kernel(double* out, double c, int iters) {

@@ -22,6 +22,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ennemi_b200.h"
@@ -33,6 +34,7 @@ namespace {
 using namespace eb2;
 
 thread_local std::string g_err;
+thread_local int g_data_flags = 0;   // bit0: NaN in the input columns, bit1: non-finite prepared data
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -69,6 +71,8 @@ struct Ctx {
   size_t pinned_cap = 0;
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
+  // device-resident columns (raw observations, noise vectors) uploaded once and referenced by key
+  std::unordered_map<uint64_t, std::pair<double*, int64_t>> cache;
 };
 
 Ctx g_ctx[kMaxDev];
@@ -395,17 +399,60 @@ double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* c
 }
 
 // ---- input staging -------------------------------------------------------------------------------
-const double* stage_coords(Scratch& s, const double* coords, int d, int64_t n, uint32_t flags, int* nonfinite_flag) {
-  const double* raw = coords;
-  if (!(flags & EB2_FLAG_DEVICE_INPUT)) {
-    double* dv = s.dev<double>(static_cast<size_t>(d) * n);
-    CU(cudaMemcpyAsync(dv, coords, sizeof(double) * d * n, cudaMemcpyHostToDevice, s.c.stream));
+// The d x n block the estimators work on comes from (a) a host block (one H2D copy), (b) a device
+// block (EB2_FLAG_DEVICE_INPUT), or (c) cached device columns, sliced / strided / rescaled by
+// prep_kernel (the reference's _rescale_data arithmetic, ennemi/_driver.py:871-902, on the device).
+struct Input {
+  const double* coords = nullptr;
+  const eb2_col_t* cols = nullptr;
+  uint32_t flags = 0;
+};
+
+const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* nonfinite_flag) {
+  const double* raw = in.coords;
+  const int64_t total = static_cast<int64_t>(d) * n;
+  if (in.cols) {
+    PrepArgs pa;
+    pa.d = d; pa.n = n; pa.flags = nonfinite_flag;
+    for (int t = 0; t < d; ++t) {
+      const eb2_col_t& c = in.cols[t];
+      auto it = s.c.cache.find(c.key);
+      if (it == s.c.cache.end()) throw CudaFail{cudaErrorInvalidValue, "column key not in the device cache", __LINE__};
+      const int64_t last = c.off + (n - 1) * c.stride;
+      if (c.off < 0 || last < 0 || c.off >= it->second.second || last >= it->second.second)
+        throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
+      PrepCol& pc = pa.col[t];
+      pc.src = it->second.first; pc.off = c.off; pc.stride = c.stride; pc.mean = c.mean; pc.std = c.std;
+      pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride;
+      if (c.nkey != 0) {
+        auto nt = s.c.cache.find(c.nkey);
+        if (nt == s.c.cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
+        const int64_t nlast = c.noff + (n - 1) * c.nstride;
+        if (c.noff < 0 || nlast < 0 || nlast >= nt->second.second)
+          throw CudaFail{cudaErrorInvalidValue, "noise slice outside the cached vector", __LINE__};
+        pc.noise = nt->second.first;
+      }
+    }
+    double* dv = s.dev<double>(static_cast<size_t>(total));
+    pa.raw = dv;
+    prep_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(pa);
+    s.launches++;
+    raw = dv;
+  } else if (!(in.flags & EB2_FLAG_DEVICE_INPUT)) {
+    double* dv = s.dev<double>(static_cast<size_t>(total));
+    CU(cudaMemcpyAsync(dv, in.coords, sizeof(double) * total, cudaMemcpyHostToDevice, s.c.stream));
     raw = dv;
   }
-  const int64_t total = static_cast<int64_t>(d) * n;
   nonfinite_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(raw, total, nonfinite_flag);
   s.launches++;
   return raw;
+}
+
+const double* stage_coords(Scratch& s, const double* coords, int d, int64_t n, uint32_t flags, int* nonfinite_flag) {
+  Input in;
+  in.coords = coords;
+  in.flags = flags;
+  return stage_input(s, in, d, n, nonfinite_flag);
 }
 
 struct Outputs {
@@ -453,7 +500,10 @@ int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs,
   CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
   CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
   c.last_launches = s.launches;
-  if (h->nonfinite) return fail(EB2_ERR_NONFINITE, "data must be finite, check for nan or inf values");
+  if (h->nonfinite) {
+    g_data_flags = h->nonfinite;
+    return fail(EB2_ERR_NONFINITE, "data must be finite, check for nan or inf values");
+  }
   if (partial) {
     for (int i = 0; i < EB2_P_LEN; ++i) partial[i] = 0.0;
     partial[EB2_P_SUM] = h->v[0];
@@ -582,6 +632,9 @@ int eb2_shutdown(void) {
     std::lock_guard<std::mutex> g2(c.mu);
     cudaSetDevice(c.dev);
     cudaStreamSynchronize(c.stream);
+    for (auto& kv : c.cache) cudaFreeAsync(kv.second.first, c.stream);
+    c.cache.clear();
+    cudaStreamSynchronize(c.stream);
     for (auto& e : c.ev) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     cudaFreeHost(c.pinned);
@@ -598,15 +651,50 @@ int eb2_last_timing(int dev, double* ms, int* launches) {
   return EB2_OK;
 }
 
+// ---- device column cache ---------------------------------------------------------------------------
+int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
+  if (key == 0 || !host || n <= 0) return fail(EB2_ERR_ARG, "eb2_cache_put: bad argument");
+  return guarded(dev, [&](Ctx& c) {
+    CU(cudaSetDevice(c.dev));
+    auto it = c.cache.find(key);
+    if (it != c.cache.end()) {
+      CU(cudaFreeAsync(it->second.first, c.stream));
+      c.cache.erase(it);
+    }
+    double* p = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(double) * n, c.stream));   // from the cached pool
+    cudaError_t e = cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);     // the caller may reuse `host` right away
+    if (e != cudaSuccess) { cudaFreeAsync(p, c.stream); throw CudaFail{e, "eb2_cache_put copy", __LINE__}; }
+    c.cache[key] = {p, n};
+    return EB2_OK;
+  });
+}
+
+int eb2_cache_drop(int dev, uint64_t key) {
+  return guarded(dev, [&](Ctx& c) {
+    CU(cudaSetDevice(c.dev));
+    if (key == 0) {
+      for (auto& kv : c.cache) cudaFreeAsync(kv.second.first, c.stream);
+      c.cache.clear();
+    } else {
+      auto it = c.cache.find(key);
+      if (it != c.cache.end()) { cudaFreeAsync(it->second.first, c.stream); c.cache.erase(it); }
+    }
+    return EB2_OK;
+  });
+}
+
+int eb2_last_data_flags(void) { return g_data_flags; }
+
 // ---- a1: KSG ------------------------------------------------------------------------------------
-int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t flags, int64_t row_lo, int64_t row_hi,
-                    double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
-  if (int rc0 = check_common(coords, n, 2, k)) return rc0;
-  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+  const uint32_t flags = in.flags;
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CallInit ci = begin_call(s);
-    const double* raw = stage_coords(s, coords, 2, n, flags, ci.nonfinite);
+    const double* raw = stage_input(s, in, 2, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
     PointSet ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1);
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
@@ -641,6 +729,24 @@ int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t fl
   });
 }
 
+int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t flags, int64_t row_lo, int64_t row_hi,
+                    double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+  if (int rc0 = check_common(coords, n, 2, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  Input in; in.coords = coords; in.flags = flags;
+  return ksg_rows_impl(dev, in, n, k, row_lo, row_hi, partial, eps_out, nx_out, ny_out);
+}
+
+int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value) {
+  if (!cols || !value) return fail(EB2_ERR_ARG, "cols/value is NULL");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2, k)) return rc0;
+  Input in; in.cols = cols; in.flags = flags & ~EB2_FLAG_DEVICE_INPUT;
+  double partial[EB2_P_LEN];
+  const int rc = ksg_rows_impl(dev, in, n, k, 0, n, partial, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  return eb2_ksg_mi_finish(partial, n, k, value);
+}
+
 int eb2_ksg_mi_finish(const double* partial, int64_t n, int k, double* value) {
   if (!partial || !value || n <= 0 || k <= 0) return fail(EB2_ERR_ARG, "bad argument");
   *value = psi_host((double)n) + psi_host((double)k) - psi_mean(partial, n);    // :113
@@ -657,16 +763,14 @@ int eb2_ksg_mi(int dev, const double* coords, int64_t n, int k, uint32_t flags, 
 }
 
 // ---- a2: Frenzel-Pompe ----------------------------------------------------------------------------
-int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uint32_t flags, int64_t row_lo,
-                 int64_t row_hi, double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
-  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  const uint32_t flags = in.flags;
   const int d = 2 + c_dim;
-  if (int rc0 = check_common(coords, n, d, k)) return rc0;
-  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CallInit ci = begin_call(s);
-    const double* raw = stage_coords(s, coords, d, n, flags, ci.nonfinite);
+    const double* raw = stage_input(s, in, d, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
     // every space on this path (xyz, xz, yz, z) contains z_0: sort by it
     PointSet ps = build_point_set(s, raw, d, n, nullptr, {}, prune ? 2 : -1);
@@ -692,6 +796,26 @@ int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uin
     export_outputs(s, ps, eps, cnts, o);
     return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
   });
+}
+
+int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uint32_t flags, int64_t row_lo,
+                 int64_t row_hi, double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+  if (int rc0 = check_common(coords, n, 2 + c_dim, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  Input in; in.coords = coords; in.flags = flags;
+  return cmi_rows_impl(dev, in, n, c_dim, k, row_lo, row_hi, partial, eps_out, nxz_out, nyz_out, nz_out);
+}
+
+int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c_dim, int k, uint32_t flags, double* value) {
+  if (!cols || !value) return fail(EB2_ERR_ARG, "cols/value is NULL");
+  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2 + c_dim, k)) return rc0;
+  Input in; in.cols = cols; in.flags = flags & ~EB2_FLAG_DEVICE_INPUT;
+  double partial[EB2_P_LEN];
+  const int rc = cmi_rows_impl(dev, in, n, c_dim, k, 0, n, partial, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  return eb2_cmi_finish(partial, n, k, value);
 }
 
 int eb2_cmi_finish(const double* partial, int64_t n, int k, double* value) {

@@ -128,6 +128,30 @@ EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, in
  * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
 EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
 
+/* ---- device-resident columns (lag sweeps and pairwise_mi upload every
+ * variable once instead of once per task; the reference's per-task _rescale_data,
+ * ennemi/_driver.py:871-902, runs on the device with host-computed mean/std and the host's
+ * fixed-seed noise vector, bit-identically) ------------------------------------------------------- */
+EB2_API int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n);  /* key != 0; replaces */
+EB2_API int eb2_cache_drop(int dev, uint64_t key);                               /* key == 0: everything */
+
+/* coordinate t of the joint space, for i in [0, n):
+ *   v_i = column[key][off + i * stride]
+ *   if (std != 0)  v_i = (v_i - mean) / std  and, if nkey != 0,  v_i += column[nkey][noff + i * nstride] */
+typedef struct eb2_col {
+  uint64_t key;
+  int64_t off, stride;
+  double mean, std;
+  uint64_t nkey;
+  int64_t noff, nstride;
+} eb2_col_t;
+
+/* a1 / a2 on cached columns: cols[0] = x, cols[1] = y, cols[2..] = condition.  On EB2_ERR_NONFINITE,
+ * eb2_last_data_flags() tells NaN input (bit0) from otherwise non-finite prepared data (bit1). */
+EB2_API int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value);
+EB2_API int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c, int k, uint32_t flags, double* value);
+EB2_API int eb2_last_data_flags(void);
+
 /* roofline denominator: FP64 (DADD) instructions per second this device retires, in 10^12/s,
  * measured with a register-resident kernel (best of 5).  The all-pairs kernels are bound by it. */
 EB2_API int eb2_measure_fp64_peak(int dev, double* tera_instr_per_s);

@@ -39,10 +39,14 @@ class OracleBackend:
     """Stands in for ``ennemi_b200._native`` in CPU tests of the HOST logic: same function
     signatures, answers computed by the CPU oracle.  Never used by the product."""
 
+    PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
+               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols")
+
     def __init__(self, backend="scipy"):
         import oracle
         self.o = oracle
         self.backend = backend
+        self.cache = {}
 
     @staticmethod
     def _rows(coords):
@@ -75,13 +79,46 @@ class OracleBackend:
     def psi(self, counts, dev=0):
         return np.asarray(self.o.psi(np.asarray(counts)), dtype=np.float64)
 
+    # ---- device column cache, emulated with numpy (same three IEEE operations as prep_kernel)
+    def cache_put(self, key, column, dev=0):
+        self.cache[(dev, key)] = np.array(column, dtype=np.float64).ravel()
+
+    def cache_drop(self, key, dev=0):
+        self.cache.pop((dev, key), None)
+
+    def _gather(self, descs, n, dev):
+        from ennemi_b200 import _native
+        rows = []
+        for d in descs:
+            col = self.cache[(dev, d.key)]
+            v = col[d.off: d.off + (n - 1) * d.stride + 1: d.stride].copy()
+            if np.isnan(v).any():
+                raise _native.NonFiniteInput("data must be finite, check for nan or inf values", True)
+            if d.std != 0.0:
+                v = (v - d.mean) / d.std
+                if d.nkey:
+                    noise = self.cache[(dev, d.nkey)]
+                    v = v + noise[d.noff: d.noff + (n - 1) * d.nstride + 1: d.nstride]
+            if not np.isfinite(v).all():
+                raise _native.NonFiniteInput("data must be finite, check for nan or inf values", False)
+            rows.append(v)
+        return rows
+
+    def ksg_mi_cols(self, descs, n, k, dev=0, flags=0):
+        x, y = self._gather(descs, n, dev)
+        return self.o.ksg_mi(x, y, k, backend=self.backend)["value"]
+
+    def cmi_cols(self, descs, n, k, dev=0, flags=0):
+        rows = self._gather(descs, n, dev)
+        return self.o.conditional_mi(rows[0], rows[1], np.column_stack(rows[2:]), k, backend=self.backend)["value"]
+
 
 @pytest.fixture
 def oracle_backend(monkeypatch):
     """Routes the estimator seam to the CPU oracle so that host logic can be tested without a GPU."""
     from ennemi_b200 import _native, _devices
     fake = OracleBackend()
-    for name in ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi"):
+    for name in OracleBackend.PATCHED:
         monkeypatch.setattr(_native, name, getattr(fake, name))
     monkeypatch.setattr(_native, "device_count", lambda: 1)
     monkeypatch.setattr(_devices, "visible", lambda: [0])

@@ -53,7 +53,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import OracleBackend
     fake = OracleBackend()
-    for name in ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi"):
+    for name in OracleBackend.PATCHED:
         setattr(nat, name, getattr(fake, name))
     _devices.visible = lambda: [0]
     x = rng.normal(size=(400, 5))

@@ -104,3 +104,29 @@ def test_analytic_values():
     z = rng.normal(size=20_000); x = z + rng.normal(size=20_000) * 0.5; y = z + rng.normal(size=20_000) * 0.5
     assert abs(eb.estimate_mi(y, x, cond=z)[0, 0]) < 0.02                   # conditionally independent
     assert eb.estimate_mi(y, x)[0, 0] > 0.3
+
+
+def test_device_column_path_on_gpu(golden_api, monkeypatch):
+    """Cached device columns + prep_kernel: (a) bit-identical to the host-prepared block through the
+    same kernels, (b) the reference's API outputs within 1e-10, (c) NaN / inf reporting."""
+    from ennemi_b200 import api, _align, _native as nat, _columns
+    rng = np.random.default_rng(3)
+    n = 50_000
+    x = rng.normal(2.0, 3.0, size=n); y = 0.4 * x + rng.normal(size=n); z = rng.normal(size=(n, 2)) + x[:, None] * 0.2
+    xs, ys, zs = _align.rescaled(x, y, z, False, False)
+    assert api.DEVICE_COLUMNS_MIN_ROWS <= n
+    assert eb.estimate_mi(y, x)[0, 0] == nat.ksg_mi(nat.pack_coords([xs, ys]), 3)            # same bits in, same bits out
+    assert eb.estimate_mi(y, x, cond=z)[0, 0] == nat.cmi(nat.pack_coords([xs, ys, zs]), 3)
+    lagged = eb.estimate_mi(y, x, lag=[0, 3, -2], cond=z, cond_lag=[[0, 1], [1, 0], [2, 2]])
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)                             # general host path
+    assert np.array_equal(lagged, eb.estimate_mi(y, x, lag=[0, 3, -2], cond=z, cond_lag=[[0, 1], [1, 0], [2, 2]]))
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    g = golden_api
+    x3, yy, cond, lags = (g["inputs"][k] for k in ("x3", "y", "cond", "lags"))
+    assert near(eb.estimate_mi(yy, x3, lags), g["mi_lags"]["out"])
+    assert near(eb.estimate_mi(yy, x3[:, :2], lags, cond=cond, cond_lag=g["mi_cond_lag2d"]["cond_lag"]), g["mi_cond_lag2d"]["out"])
+    assert near(eb.pairwise_mi(np.column_stack((x3, yy, cond[:, 0])), k=4), g["pairwise5"]["out"])
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_mi(np.where(np.arange(600) == 5, np.nan, yy), x3)
+    with pytest.raises(ValueError, match="data must be finite"):
+        eb.estimate_mi(yy, np.where(np.arange(600) == 7, np.inf, x3[:, 0]), preprocess=False)

@@ -182,3 +182,59 @@ def test_seam_signatures_match_reference(oracle_backend):
     assert e._estimate_single_entropy(z, 3) == oracle.knn_entropy(z, 3, backend="scipy")["value"]
     assert e._estimate_single_entropy(x[::2], 3) == oracle.knn_entropy(x[::2], 3, backend="scipy")["value"]   # strided view
     assert np.isinf(e._psi(np.array([1, 0])))
+
+
+def test_device_column_path_gives_identical_results(oracle_backend, golden_api, monkeypatch):
+    """Lag sweeps / pairwise on cached device columns (rescaling done by the device's prep kernel,
+    emulated here with the same IEEE operations) must reproduce the reference bit for bit, including
+    cond_lag windows, the noise draw order and constant-data handling."""
+    from ennemi_b200 import api
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    g = golden_api
+    x3, y, cond, lags = (g["inputs"][k] for k in ("x3", "y", "cond", "lags"))
+    ynan, xnan = g["mi_dropnan"]["ynan"], g["mi_dropnan"]["xnan"]
+    data5 = np.column_stack((x3, y, cond[:, 0]))
+    puts = []
+    real_put = oracle_backend.cache_put
+    monkeypatch.setattr(eb.api._columns._native, "cache_put", lambda key, col, dev=0: (puts.append(key), real_put(key, col, dev))[1])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert eq(eb.estimate_mi(y, x3, lags), g["mi_lags"]["out"])
+        assert len(puts) >= 4                                           # the fast path really ran
+        assert eq(eb.estimate_mi(y, x3, lags, k=5, preprocess=False), g["mi_lags_k5_nopre"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond), g["mi_cond"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=1), g["mi_cond_lag1"]["out"])
+        assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=g["mi_cond_lag2d"]["cond_lag"]), g["mi_cond_lag2d"]["out"])
+        assert eq(eb.estimate_corr(y, x3, lags), g["corr_lags"]["out"])
+        assert eq(eb.pairwise_mi(x3), g["pairwise"]["out"])
+        assert eq(eb.pairwise_mi(data5, k=4), g["pairwise5"]["out"])
+        assert eq(eb.pairwise_corr(data5), g["pairwise5_corr"]["out"])
+        # NaNs present: drop_nan is not a no-op -> general path; without drop_nan -> the reference's error
+        assert eq(eb.estimate_mi(ynan, xnan, [0, 1], drop_nan=True), g["mi_dropnan"]["out"])
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_mi(ynan, x3)
+    with pytest.raises(ValueError, match="data must be finite"):
+        eb.estimate_mi(y, np.where(np.arange(600) == 7, np.inf, x3[:, 0]), preprocess=False)
+    with pytest.raises(TypeError):
+        eb.estimate_mi(y, x3[:, 0], lag=1.5)
+    with pytest.raises(ValueError, match="k must be smaller"):
+        eb.estimate_mi(y[:5], x3[:5, 0], k=5)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        out = eb.estimate_mi(y, np.column_stack((np.full(600, 2.0), x3[:, 0])), preprocess=True)
+    # a constant x consumes no noise draw: the second variable must still match the plain call bit for bit
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)      # the general host path must agree bit for bit
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert eq(out, eb.estimate_mi(y, np.column_stack((np.full(600, 2.0), x3[:, 0])), preprocess=True))
+    assert oracle_backend.cache == {} or all(k[1] in eb.api._columns.NoiseBank._keys.values() for k in oracle_backend.cache)
+
+
+def test_window_stats_bits():
+    from ennemi_b200._columns import window_stats
+    rng = np.random.default_rng(1)
+    for n in (5, 8, 127, 128, 129, 1000, 4097, 100_003):
+        a = rng.normal(3.0, 2.5, size=(n, 3))
+        for view in (np.ascontiguousarray(a[:, 0]), a[:, 1], a[::2, 2], a[3:, 0]):
+            if len(view):
+                m, s = window_stats(view)
+                assert m == view.mean() and s == view.std()

@@ -21,7 +21,7 @@ DRIVER = textwrap.dedent("""
     from ennemi_b200 import _native, _devices, _estimators
     from conftest import OracleBackend
     fake = OracleBackend()
-    for name in ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi"):
+    for name in OracleBackend.PATCHED:
         setattr(_native, name, getattr(fake, name))
     _native.device_count = lambda: 1
     _devices.visible = lambda: [0]
@@ -33,9 +33,14 @@ DRIVER = textwrap.dedent("""
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference tree not mounted")
-@pytest.mark.parametrize("suite", ["unit", "pandas", "integration"])
-def test_reference_suite_passes_on_our_host_logic(suite):
+@pytest.mark.parametrize("suite,min_rows", [("unit", None), ("pandas", None), ("integration", None),
+                                            ("unit", "0"), ("pandas", "0")])
+def test_reference_suite_passes_on_our_host_logic(suite, min_rows):
+    """min_rows="0" forces the device-column path (cached columns + device-side rescaling, emulated
+    by the oracle backend) for every eligible call, so the reference's tests cover it as well."""
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    if min_rows is not None:
+        env["ENNEMI_B200_COLUMNS_MIN_ROWS"] = min_rows
     proc = subprocess.run([sys.executable, "-c", DRIVER.format(root=ROOT), os.path.join(REF_TESTS, suite)],
                           capture_output=True, text=True, env=env, cwd="/tmp", timeout=900)
     tail = (proc.stdout + proc.stderr)[-2000:]
