@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads) psi_kernel(const PsiArgs a) {
     const Tile tile = a.tiles[tile_id];
     double sum = 0.0, za = 0.0, zb = 0.0, zc = 0.0;
 #pragma unroll
-    for (int i = 0; i < kQpt; ++i) {
+    for (int i = 0; i < kMaxQpt; ++i) {
       const int qi = threadIdx.x + i * kThreads;
       if (qi < tile.q_n) {
         const int slot = tile.q_lo + qi;

@@ -7,8 +7,9 @@ namespace eb2 {
 
 constexpr int kMaxDim = 12;        // EB2_MAX_DIM
 constexpr int kThreads = 256;      // threads per CTA in the all-pairs kernels
-constexpr int kQpt = 2;            // query rows per thread
-constexpr int kTileQ = kThreads * kQpt;   // query rows per CTA tile
+constexpr int kMaxQpt = 2;         // query rows per thread: 2 (512-row tiles) for large sets, 1 (256-row tiles)
+                                   // when the set is too small to fill the 148 SMs with 512-row tiles
+__host__ __device__ constexpr int tile_rows(int qpt) { return kThreads * qpt; }
 constexpr int kSegAlign = 16;      // segments start on 16-slot (128 B) boundaries: TMA bulk copies need 16 B
 
 // Candidate-chunk length (slots) staged in shared memory per step, by dimension of the space.
@@ -17,7 +18,7 @@ __host__ __device__ constexpr int chunk_len(int d) { return d <= 2 ? 512 : (d <=
 // One tile of query rows and the candidate segment it is compared against.
 struct Tile {
   int q_lo;      // first query slot
-  int q_n;       // valid query rows in the tile (<= kTileQ); slots past it are NaN padding
+  int q_n;       // valid query rows in the tile (<= tile_rows(qpt)); slots past it are NaN padding
   int c_lo;      // first candidate slot of the segment (multiple of kSegAlign)
   int c_len;     // valid candidate rows in the segment (the padded tail up to the next multiple of 16 is NaN)
 };

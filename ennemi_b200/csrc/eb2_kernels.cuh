@@ -56,7 +56,7 @@ struct KnnArgs {
   int k;                 // result = (k+1)-th smallest, i.e. best[k]
   int sort_row;          // row of P sorted ascending inside every segment (enables pruning), or -1
   double* eps;           // out, per query slot
-  double* heap;          // scratch for the large-k variant: [k+1][gridDim.x * kTileQ]
+  double* heap;          // scratch for the large-k variant: [k+1][gridDim.x * tile_rows(QPT)]
   unsigned long long* pairs;  // work counter (pairs evaluated)
   int ntiles;
   // straggler deferral (pruned mode, register top-k variants): when fewer than `defer_below` threads of a
@@ -137,10 +137,12 @@ struct HeapRef {
 // Bitonic sort of the kTileQ per-query keys (ascending) in shared memory; afterwards rank r holds the
 // home index sidx[r] of the query with the r-th smallest key.  Used to make warps homogeneous in
 // search radius so that whole warps can skip candidate chunks (exact pruning at warp granularity).
+template <int NQ>
 __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
   const int tid = threadIdx.x;
-  for (int k = 2; k <= kTileQ; k <<= 1) {
+  for (int k = 2; k <= NQ; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
+      if (tid < NQ / 2) {
       const int i = 2 * j * (tid / j) + (tid % j);
       const int l = i + j;
       const bool up = (i & k) == 0;
@@ -149,35 +151,37 @@ __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
         skey[i] = b; skey[l] = a;
         const int t = sidx[i]; sidx[i] = sidx[l]; sidx[l] = t;
       }
+      }
       __syncthreads();
     }
   }
 }
 
 // moves one per-query double from its home thread to the thread that owns the query after sorting
-__device__ __forceinline__ void cta_permute(double* xch, const int (&src)[kQpt], double (&v)[kQpt]) {
+template <int QPT>
+__device__ __forceinline__ void cta_permute(double* xch, const int (&src)[QPT], double (&v)[QPT]) {
 #pragma unroll
-  for (int i = 0; i < kQpt; ++i) xch[threadIdx.x + i * kThreads] = v[i];
+  for (int i = 0; i < QPT; ++i) xch[threadIdx.x + i * kThreads] = v[i];
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kQpt; ++i) v[i] = xch[src[i]];
+  for (int i = 0; i < QPT; ++i) v[i] = xch[src[i]];
   __syncthreads();
 }
 
 // candidates tested per branch in the all-pairs inner loops (register budget: 2*G*D for the group)
 __host__ __device__ constexpr int group_len(int d) { return d <= 2 ? 4 : 2; }
 // resident CTAs per SM the kernels are compiled for, from a register estimate:
-// queries 4*D + lists 4*K1T + candidate group 2*G*D + ~34 bookkeeping
-__host__ __device__ constexpr int knn_min_blocks(int d, int k1t) {
-  const int regs = 4 * d + 4 * k1t + 2 * group_len(d) * d + 40;
+// queries 2*QPT*D + lists 2*QPT*K1T + candidate group 2*G*D + ~40 bookkeeping
+__host__ __device__ constexpr int knn_min_blocks(int d, int k1t, int qpt) {
+  const int regs = 2 * qpt * d + 2 * qpt * k1t + 2 * group_len(d) * d + 40;
   return regs <= 80 ? 3 : (regs <= 128 ? 2 : 1);
 }
 
 // all queries of one thread against one staged candidate chunk (shared memory, broadcast LDS.128)
-template <int D, int K1T, int TC>
-__device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, const double (&q)[kQpt][D],
-                                               double (&best)[kQpt][(K1T > 0 ? K1T : 1)], double (&thr)[kQpt],
-                                               const HeapRef (&heap)[kQpt]) {
+template <int D, int K1T, int TC, int QPT>
+__device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, const double (&q)[QPT][D],
+                                               double (&best)[QPT][(K1T > 0 ? K1T : 1)], double (&thr)[QPT],
+                                               const HeapRef (&heap)[QPT]) {
   constexpr int kGroup = group_len(D);
 #pragma unroll 1
   for (int jj = 0; jj < len; jj += kGroup) {
@@ -194,7 +198,7 @@ __device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, cons
         }
       }
 #pragma unroll
-      for (int i = 0; i < kQpt; ++i) {
+      for (int i = 0; i < QPT; ++i) {
 #pragma unroll
         for (int u = 0; u < kGroup; ++u) any = any | inside_lt<D>(q[i], c[u], thr[i]);
       }
@@ -207,7 +211,7 @@ __device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, cons
 #pragma unroll
         for (int t = 0; t < D; ++t) cu[t] = sbuf[t * TC + jj + u];
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) {
+        for (int i = 0; i < QPT; ++i) {
           if (inside_lt<D>(q[i], cu, thr[i])) {
             const double m = cheb<D>(q[i], cu);
             if constexpr (K1T > 0) { topk_insert<K1T>(best[i], m); thr[i] = best[i][K1T - 1]; }
@@ -220,8 +224,9 @@ __device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, cons
 }
 
 // K1T > 0: register-resident sorted top-K1T (k+1 <= K1T).  K1T == 0: heap in global scratch, any k.
-template <int D, int K1T>
-__global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(const KnnArgs a) {
+template <int D, int K1T, int QPT>
+__global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_kernel(const KnnArgs a) {
+  constexpr int kTileQ = tile_rows(QPT);
   constexpr int TC = chunk_len(D);
   constexpr int kGroup = group_len(D);
   constexpr int NB = (K1T > 0 ? K1T : 1);
@@ -243,15 +248,15 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
   for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = a.tiles[tile_id];
 
-    double q[kQpt][D];
-    double best[kQpt][NB];
-    double thr[kQpt];
-    int qslot[kQpt];          // position of the query inside the tile
-    int rstart[kQpt], lend[kQpt];   // deferred remainder of the search (segment-relative slots)
-    bool valid[kQpt];
-    HeapRef heap[kQpt];
+    double q[QPT][D];
+    double best[QPT][NB];
+    double thr[QPT];
+    int qslot[QPT];          // position of the query inside the tile
+    int rstart[QPT], lend[QPT];   // deferred remainder of the search (segment-relative slots)
+    bool valid[QPT];
+    HeapRef heap[QPT];
 #pragma unroll
-    for (int i = 0; i < kQpt; ++i) {
+    for (int i = 0; i < QPT; ++i) {
       const int qi = tid + i * kThreads;
       qslot[i] = qi;
       rstart[i] = tile.c_len;
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
       for (int j = 0; j < nchunks; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
+        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
         __syncthreads();   // everyone is done with sbuf before the next bulk copy lands in it
       }
     } else {
@@ -299,50 +304,50 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
       for (int j = home_lo; j <= home_hi; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
+        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
         __syncthreads();
       }
       if (home_lo > 0 || home_hi + 1 < nchunks) {
         // 2. regroup the tile's queries by current k-th distance: warp w gets ranks [64w, 64w+64)
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) {
+        for (int i = 0; i < QPT; ++i) {
           xch[tid + i * kThreads] = valid[i] ? thr[i] : 0.0;
           sidx[tid + i * kThreads] = tid + i * kThreads;
         }
         __syncthreads();
-        cta_sort_keys(xch, sidx);
-        int src[kQpt];
+        cta_sort_keys<kTileQ>(xch, sidx);
+        int src[QPT];
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) src[i] = sidx[kQpt * tid + i];
+        for (int i = 0; i < QPT; ++i) src[i] = sidx[QPT * tid + i];
         __syncthreads();
 #pragma unroll
         for (int t = 0; t < D; ++t) {
-          double v[kQpt];
+          double v[QPT];
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) v[i] = q[i][t];
-          cta_permute(xch, src, v);
+          for (int i = 0; i < QPT; ++i) v[i] = q[i][t];
+          cta_permute<QPT>(xch, src, v);
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) q[i][t] = v[i];
+          for (int i = 0; i < QPT; ++i) q[i][t] = v[i];
         }
         if constexpr (K1T > 0) {
 #pragma unroll
           for (int t = 0; t < K1T; ++t) {
-            double v[kQpt];
+            double v[QPT];
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i) v[i] = best[i][t];
-            cta_permute(xch, src, v);
+            for (int i = 0; i < QPT; ++i) v[i] = best[i][t];
+            cta_permute<QPT>(xch, src, v);
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i) best[i][t] = v[i];
+            for (int i = 0; i < QPT; ++i) best[i][t] = v[i];
           }
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) thr[i] = best[i][K1T - 1];
+          for (int i = 0; i < QPT; ++i) thr[i] = best[i][K1T - 1];
         } else {
-          cta_permute(xch, src, thr);
+          cta_permute<QPT>(xch, src, thr);
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) heap[i].base = a.heap + (int64_t)blockIdx.x * kTileQ + src[i];
+          for (int i = 0; i < QPT; ++i) heap[i].base = a.heap + (int64_t)blockIdx.x * kTileQ + src[i];
         }
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) {
+        for (int i = 0; i < QPT; ++i) {
           qslot[i] = src[i];
           valid[i] = src[i] < tile.q_n;
         }
@@ -354,20 +359,20 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
           const double cmin = srow[j * TC];
           bool need = false;
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) need = need || (valid[i] && !((cmin - q[i][0]) >= thr[i]));
+          for (int i = 0; i < QPT; ++i) need = need || (valid[i] && !((cmin - q[i][0]) >= thr[i]));
           const bool wneed = __any_sync(0xffffffffu, need);
           const int nneed = __syncthreads_count(need);
           if (nneed == 0) break;
           if (nneed < a.defer_below) {   // stragglers: hand the rest of this direction to the leftover kernel
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i)
+            for (int i = 0; i < QPT; ++i)
               if (valid[i] && !((cmin - q[i][0]) >= thr[i])) rstart[i] = j * TC;
             break;
           }
           const int len = fetch_chunk(j);
           if (wneed) {
-            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
-            knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
+            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * QPT;
+            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -375,20 +380,20 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
           const double cmax = srow[min((j + 1) * TC, tile.c_len) - 1];
           bool need = false;
 #pragma unroll
-          for (int i = 0; i < kQpt; ++i) need = need || (valid[i] && !((q[i][0] - cmax) >= thr[i]));
+          for (int i = 0; i < QPT; ++i) need = need || (valid[i] && !((q[i][0] - cmax) >= thr[i]));
           const bool wneed = __any_sync(0xffffffffu, need);
           const int nneed = __syncthreads_count(need);
           if (nneed == 0) break;
           if (nneed < a.defer_below) {
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i)
+            for (int i = 0; i < QPT; ++i)
               if (valid[i] && !((q[i][0] - cmax) >= thr[i])) lend[i] = min((j + 1) * TC, tile.c_len);
             break;
           }
           const int len = fetch_chunk(j);
           if (wneed) {
-            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * kQpt;
-            knn_scan_chunk<D, K1T, TC>(sbuf, len, q, best, thr, heap);
+            if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * QPT;
+            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T)) knn_kernel(c
     }
 
 #pragma unroll
-    for (int i = 0; i < kQpt; ++i) {
+    for (int i = 0; i < QPT; ++i) {
       if (valid[i]) {
         double r;
         if constexpr (K1T > 0) {
@@ -581,8 +586,9 @@ __device__ __forceinline__ int upper_bound_gt(const double* a, int len, double v
   return lo;
 }
 
-template <int C, int E>
-__global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kernel(const CountArgs a) {
+template <int C, int E, int QPT>
+__global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count_kernel(const CountArgs a) {
+  constexpr int kTileQ = tile_rows(QPT);
   constexpr int D = C + E;
   constexpr int TC = chunk_len(D);
   constexpr int kGroup = group_len(D);
@@ -610,14 +616,14 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
 
   for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = a.tiles[tile_id];
-    double qs[kQpt][CS];
-    double qe[kQpt][ES];
-    double r[kQpt];
-    int ns[kQpt], ne0[kQpt], ne1[kQpt];
-    int qslot[kQpt];
-    bool valid[kQpt];
+    double qs[QPT][CS];
+    double qe[QPT][ES];
+    double r[QPT];
+    int ns[QPT], ne0[QPT], ne1[QPT];
+    int qslot[QPT];
+    bool valid[QPT];
 #pragma unroll
-    for (int i = 0; i < kQpt; ++i) {
+    for (int i = 0; i < QPT; ++i) {
       const int qi = tid + i * kThreads;
       qslot[i] = qi;
       valid[i] = qi < tile.q_n;
@@ -637,37 +643,37 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
       // the pruning coordinate is the first shared one (or the only extra one): host guarantees it
       // 1. regroup the tile's queries by radius so that warps are homogeneous
 #pragma unroll
-      for (int i = 0; i < kQpt; ++i) {
+      for (int i = 0; i < QPT; ++i) {
         xch[tid + i * kThreads] = valid[i] ? r[i] : -kInf;
         sidx[tid + i * kThreads] = tid + i * kThreads;
       }
       __syncthreads();
-      cta_sort_keys(xch, sidx);
-      int src[kQpt];
+      cta_sort_keys<kTileQ>(xch, sidx);
+      int src[QPT];
 #pragma unroll
-      for (int i = 0; i < kQpt; ++i) src[i] = sidx[kQpt * tid + i];
+      for (int i = 0; i < QPT; ++i) src[i] = sidx[QPT * tid + i];
       __syncthreads();
 #pragma unroll
       for (int t = 0; t < C; ++t) {
-        double v[kQpt];
+        double v[QPT];
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) v[i] = qs[i][t];
-        cta_permute(xch, src, v);
+        for (int i = 0; i < QPT; ++i) v[i] = qs[i][t];
+        cta_permute<QPT>(xch, src, v);
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) qs[i][t] = v[i];
+        for (int i = 0; i < QPT; ++i) qs[i][t] = v[i];
       }
 #pragma unroll
       for (int t = 0; t < E; ++t) {
-        double v[kQpt];
+        double v[QPT];
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) v[i] = qe[i][t];
-        cta_permute(xch, src, v);
+        for (int i = 0; i < QPT; ++i) v[i] = qe[i][t];
+        cta_permute<QPT>(xch, src, v);
 #pragma unroll
-        for (int i = 0; i < kQpt; ++i) qe[i][t] = v[i];
+        for (int i = 0; i < QPT; ++i) qe[i][t] = v[i];
       }
-      cta_permute(xch, src, r);
+      cta_permute<QPT>(xch, src, r);
 #pragma unroll
-      for (int i = 0; i < kQpt; ++i) {
+      for (int i = 0; i < QPT; ++i) {
         qslot[i] = src[i];
         valid[i] = src[i] < tile.q_n;
       }
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
       //    rounded subtraction in the exact test can never disagree with them.
       double vmin = kInf, vmax = -kInf, rmax = -kInf;
 #pragma unroll
-      for (int i = 0; i < kQpt; ++i) {
+      for (int i = 0; i < QPT; ++i) {
         if (valid[i]) {
           const double v = (C > 0) ? qs[i][0] : qe[i][0];
           vmin = fmin(vmin, v);
@@ -717,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
       __syncthreads();
     }
     unsigned long long npairs = 0;
+    const bool dense_hits = a.prune_b_row >= 0;
 
     for (int j = ch_lo; j < ch_hi; ++j) {
       const int c_off = j * TC;
@@ -725,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
       mbar_wait(&bar, phase);
       phase ^= 1;
       if (j >= w_lo && j < w_hi) {
-        if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - c_off) * 32 * kQpt;
+        if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - c_off) * 32 * QPT;
 #pragma unroll 1
         for (int jj = 0; jj < len; jj += kGroup) {
           double c[kGroup][D];
@@ -738,12 +745,29 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
               c[u + 1][t] = v.y;
             }
           }
-          if constexpr (C > 0) {
+          if (C > 0 && dense_hits) {
+            // windowed (pruned) scan: a neighbour turns up in nearly every group of some lane, so the
+            // early-out branch below would be taken all the time; count everything branch-free instead
+            if constexpr (C > 0) {
+#pragma unroll
+              for (int i = 0; i < QPT; ++i) {
+#pragma unroll
+                for (int u = 0; u < kGroup; ++u) {
+                  bool in = fabs(qs[i][0] - c[u][0]) <= r[i];
+#pragma unroll
+                  for (int t = 1; t < C; ++t) in = in && (fabs(qs[i][t] - c[u][t]) <= r[i]);
+                  ns[i] += (int)in;
+                  if constexpr (E > 0) ne0[i] += (int)(in && fabs(qe[i][0] - c[u][C]) <= r[i]);
+                  if constexpr (E > 1) ne1[i] += (int)(in && fabs(qe[i][1] - c[u][C + 1]) <= r[i]);
+                }
+              }
+            }
+          } else if constexpr (C > 0) {
             // the shared coordinates decide; the private ones are only looked at for pairs that pass
-            bool h[kQpt][kGroup];
+            bool h[QPT][kGroup];
             bool any = false;
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i) {
+            for (int i = 0; i < QPT; ++i) {
 #pragma unroll
               for (int u = 0; u < kGroup; ++u) {
                 bool in = fabs(qs[i][0] - c[u][0]) <= r[i];
@@ -755,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
             }
             if (any) {
 #pragma unroll
-              for (int i = 0; i < kQpt; ++i) {
+              for (int i = 0; i < QPT; ++i) {
 #pragma unroll
                 for (int u = 0; u < kGroup; ++u) {
                   ns[i] += (int)h[i][u];
@@ -766,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < kQpt; ++i) {
+            for (int i = 0; i < QPT; ++i) {
 #pragma unroll
               for (int u = 0; u < kGroup; ++u) {
                 if constexpr (E > 0) ne0[i] += (int)(fabs(qe[i][0] - c[u][0]) <= r[i]);
@@ -780,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2)) count_kern
     }
 
 #pragma unroll
-    for (int i = 0; i < kQpt; ++i) {
+    for (int i = 0; i < QPT; ++i) {
       if (valid[i]) {
         const int slot = tile.q_lo + qslot[i];
         if constexpr (C > 0) a.cnt_s[slot] = ns[i];

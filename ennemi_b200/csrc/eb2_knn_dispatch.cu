@@ -9,13 +9,17 @@ int knn_grid(int k, int ntiles, int sm_count) {
   return ntiles < cap ? ntiles : cap;
 }
 
-template <int D>
-static cudaError_t launch_d(const KnnArgs& a, int grid, cudaStream_t s) {
+template <int D, int QPT>
+static cudaError_t launch_dq(const KnnArgs& a, int grid, cudaStream_t s) {
   const int k1 = a.k + 1;
-  if (k1 <= 4) knn_kernel<D, 4><<<grid, kThreads, 0, s>>>(a);
-  else if (k1 <= 8) knn_kernel<D, 8><<<grid, kThreads, 0, s>>>(a);
-  else knn_kernel<D, 0><<<grid, kThreads, 0, s>>>(a);
+  if (k1 <= 4) knn_kernel<D, 4, QPT><<<grid, kThreads, 0, s>>>(a);
+  else if (k1 <= 8) knn_kernel<D, 8, QPT><<<grid, kThreads, 0, s>>>(a);
+  else knn_kernel<D, 0, QPT><<<grid, kThreads, 0, s>>>(a);
   return cudaGetLastError();
+}
+template <int D>
+static cudaError_t launch_d(int qpt, const KnnArgs& a, int grid, cudaStream_t s) {
+  return qpt == 1 ? launch_dq<D, 1>(a, grid, s) : launch_dq<D, 2>(a, grid, s);
 }
 
 template <int D>
@@ -45,20 +49,20 @@ cudaError_t launch_knn_leftover(int D, const KnnArgs& a, int grid, cudaStream_t 
   }
 }
 
-cudaError_t launch_knn(int D, const KnnArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_knn(int D, int qpt, const KnnArgs& a, int grid, cudaStream_t s) {
   switch (D) {
-    case 1: return launch_d<1>(a, grid, s);
-    case 2: return launch_d<2>(a, grid, s);
-    case 3: return launch_d<3>(a, grid, s);
-    case 4: return launch_d<4>(a, grid, s);
-    case 5: return launch_d<5>(a, grid, s);
-    case 6: return launch_d<6>(a, grid, s);
-    case 7: return launch_d<7>(a, grid, s);
-    case 8: return launch_d<8>(a, grid, s);
-    case 9: return launch_d<9>(a, grid, s);
-    case 10: return launch_d<10>(a, grid, s);
-    case 11: return launch_d<11>(a, grid, s);
-    case 12: return launch_d<12>(a, grid, s);
+    case 1: return launch_d<1>(qpt, a, grid, s);
+    case 2: return launch_d<2>(qpt, a, grid, s);
+    case 3: return launch_d<3>(qpt, a, grid, s);
+    case 4: return launch_d<4>(qpt, a, grid, s);
+    case 5: return launch_d<5>(qpt, a, grid, s);
+    case 6: return launch_d<6>(qpt, a, grid, s);
+    case 7: return launch_d<7>(qpt, a, grid, s);
+    case 8: return launch_d<8>(qpt, a, grid, s);
+    case 9: return launch_d<9>(qpt, a, grid, s);
+    case 10: return launch_d<10>(qpt, a, grid, s);
+    case 11: return launch_d<11>(qpt, a, grid, s);
+    case 12: return launch_d<12>(qpt, a, grid, s);
     default: return cudaErrorInvalidValue;
   }
 }

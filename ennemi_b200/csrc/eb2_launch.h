@@ -5,11 +5,12 @@
 
 namespace eb2 {
 // D = dimension of the search space (1..kMaxDim); k+1 <= 8 uses the register top-k variants,
-// larger k the heap variant (args.heap must then hold (k+1) * grid * kTileQ doubles).
-cudaError_t launch_knn(int D, const KnnArgs& args, int grid, cudaStream_t stream);
+// larger k the heap variant (args.heap must then hold (k+1) * grid * tile_rows(qpt) doubles).
+// qpt = query rows per thread (1 or 2): tiles are tile_rows(qpt) rows
+cudaError_t launch_knn(int D, int qpt, const KnnArgs& args, int grid, cudaStream_t stream);
 int knn_grid(int k, int ntiles, int sm_count);
 // finishes the queries knn_kernel deferred (register top-k variants only)
 cudaError_t launch_knn_leftover(int D, const KnnArgs& args, int grid, cudaStream_t stream);
 // C shared + E private coordinates
-cudaError_t launch_count(int C, int E, const CountArgs& args, int grid, cudaStream_t stream);
+cudaError_t launch_count(int C, int E, int qpt, const CountArgs& args, int grid, cudaStream_t stream);
 }  // namespace eb2

@@ -145,6 +145,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // ---- the point set -----------------------------------------------------------------------------
 struct PointSet {
+  int qpt = kMaxQpt;          // query rows per thread of the all-pairs kernels: tiles are tile_rows(qpt) rows
   double* P = nullptr;
   int64_t stride = 0;
   int d = 0;
@@ -177,6 +178,8 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   ps.d = d;
   ps.n = n;
   ps.sort_row = sort_row;
+  // 512-row tiles only when they still give every SM several CTAs; smaller sets use 256-row tiles
+  ps.qpt = (n / tile_rows(kMaxQpt) >= 4 * static_cast<int64_t>(s.c.sm_count)) ? kMaxQpt : 1;
   const int nseg = cls ? static_cast<int>(class_size.size()) : 1;
   std::vector<int> seg_rank(nseg);
   ps.seg_slot.resize(nseg);
@@ -265,8 +268,9 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
   std::vector<Tile> t;
   int64_t rank = 0, rows = 0;
   for (size_t g = 0; g < ps.seg_slot.size(); ++g) {
-    for (int off = 0; off < ps.seg_len[g]; off += kTileQ) {
-      const int qn = std::min(kTileQ, ps.seg_len[g] - off);
+    const int tq = tile_rows(ps.qpt);
+    for (int off = 0; off < ps.seg_len[g]; off += tq) {
+      const int qn = std::min(tq, ps.seg_len[g] - off);
       if (rank >= row_lo && rank < row_hi) {
         Tile x;
         x.q_lo = ps.seg_slot[g] + off;
@@ -331,8 +335,8 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
     CU(cudaMemsetAsync(a.left_count, 0, sizeof(unsigned int), s.c.stream));
   }
   const int grid = knn_grid(k, ts.count, s.c.sm_count);
-  if (k + 1 > 8) a.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * kTileQ);
-  CU(launch_knn(D, a, grid, s.c.stream));
+  if (k + 1 > 8) a.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * tile_rows(ps.qpt));
+  CU(launch_knn(D, ps.qpt, a, grid, s.c.stream));
   s.launches++;
   if (a.defer_below > 0) {
     // entry count stays on the device: a fixed persistent grid walks the list
@@ -370,7 +374,7 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
     if (C == 0 && E == 1 && b_erow.row[0] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_erow.row[0]; }
   }
   a.cnt_s = out.s; a.cnt_e0 = out.e0; a.cnt_e1 = out.e1; a.pairs = pairs;
-  CU(launch_count(C, E, a, ts.count, s.c.stream));
+  CU(launch_count(C, E, qs.qpt, a, ts.count, s.c.stream));
   s.launches++;
 }
 
