@@ -65,6 +65,7 @@ class NoiseBank:
 
     @classmethod
     def key_for(cls, shapes: tuple, values: np.ndarray, dev: int) -> int:
+        ordinal = _devices.ordinal(dev)
         with cls._lock:
             key = cls._keys.get(shapes)
             if key is None:
@@ -78,7 +79,7 @@ class NoiseBank:
                             _native.cache_drop(old, dev=d)
             else:
                 cls._keys.move_to_end(shapes)
-            have = cls._on_device.setdefault(dev, set())
+            have = cls._on_device.setdefault(ordinal, set())
             if key not in have:
                 _native.cache_put(key, np.ravel(values), dev=dev)
                 have.add(key)
@@ -101,7 +102,7 @@ class ColumnStore:
 
     def ensure(self, dev: int, key: int) -> None:
         with self._lock:
-            have = self._on_device.setdefault(dev, set())
+            have = self._on_device.setdefault(_devices.ordinal(dev), set())
             if key not in have:
                 _native.cache_put(key, self._cols[key], dev=dev)
                 have.add(key)

@@ -43,6 +43,18 @@ def use(dev: int):
         _tls.dev = prev
 
 
+LANES = 3    # concurrent streams per GPU used by the task fan-out (the library supports up to 4)
+
+
+def ordinal(dev: int) -> int:
+    """CUDA device ordinal of a (device | lane << 8) id."""
+    return dev & 0xFF
+
+
+def with_lane(dev: int, lane: int) -> int:
+    return ordinal(dev) | ((lane % 4) << 8)
+
+
 def visible() -> List[int]:
     """Devices a task fan-out may use from this process.
 

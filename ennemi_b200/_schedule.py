@@ -5,9 +5,9 @@ and keeps its contract: results come back in task order, ``callback(i)`` fires o
 task (from the worker that ran it), ``max_threads`` bounds the concurrency, and a workload that is
 too small to be worth it runs inline on the calling thread.
 
-Each worker thread is bound to one GPU.  Two workers share a GPU so that one task's host-side
-preparation (lag slicing, rescaling, noise) overlaps the other's kernels; calls on one device
-serialise inside the library.  A task's value never depends on which worker ran it (the device
+Each worker thread is bound to one GPU and one of that GPU's stream lanes.  Several workers share
+a GPU so that one task's host-side preparation overlaps another's kernels and so that tasks too
+small to fill 148 SMs run side by side on separate streams.  A task's value never depends on which worker ran it (the device
 reduction is a fixed tree), so results are bitwise reproducible.
 """
 from __future__ import annotations
@@ -19,7 +19,7 @@ from . import _devices
 
 T = TypeVar("T")
 
-WORKERS_PER_DEVICE = 2
+WORKERS_PER_DEVICE = _devices.LANES
 INLINE_BUDGET_S = 0.05   # run inline when the whole job is estimated below this
 
 
@@ -57,7 +57,9 @@ def run_tasks(func: Callable[[T], float], params: Sequence[T], max_threads: Opti
         callback(i)
 
     with concurrent.futures.ThreadPoolExecutor(workers, "ennemi-b200-work") as pool:
-        futures = [pool.submit(work, i, devices[i % len(devices)]) for i in range(len(params))]
+        # task i -> device i mod G; consecutive tasks of one device rotate over its stream lanes
+        futures = [pool.submit(work, i, _devices.with_lane(devices[i % len(devices)], (i // len(devices)) % _devices.LANES))
+                   for i in range(len(params))]
         concurrent.futures.wait(futures)
         for f in futures:
             f.result()          # re-raise the first failure, like the reference's done-callback does

@@ -58,7 +58,16 @@ struct CudaFail {
   } while (0)
 
 constexpr int kMaxDev = 64;
+constexpr int kMaxLanes = 4;       // independent streams ("lanes") per device: `dev` = ordinal | lane << 8
 constexpr int kNumEvents = 8;
+
+// device-resident columns (raw observations, noise vectors) uploaded once and referenced by key;
+// shared by the lanes of a device
+struct DevShared {
+  std::mutex mu;
+  std::unordered_map<uint64_t, std::pair<double*, int64_t>> cache;
+};
+DevShared g_shared[kMaxDev];
 
 struct Ctx {
   int dev = -1;
@@ -71,16 +80,16 @@ struct Ctx {
   size_t pinned_cap = 0;
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
-  // device-resident columns (raw observations, noise vectors) uploaded once and referenced by key
-  std::unordered_map<uint64_t, std::pair<double*, int64_t>> cache;
+  DevShared* shared = nullptr;
 };
 
-Ctx g_ctx[kMaxDev];
+Ctx g_ctx[kMaxDev * kMaxLanes];
 std::mutex g_init_mu;
 
-Ctx& get_ctx(int dev) {
-  if (dev < 0 || dev >= kMaxDev) throw CudaFail{cudaErrorInvalidDevice, "device index", __LINE__};
-  Ctx& c = g_ctx[dev];
+Ctx& get_ctx(int dev_lane) {
+  const int dev = dev_lane & 0xff, lane = (dev_lane >> 8) & 0xff;
+  if (dev_lane < 0 || dev >= kMaxDev || lane >= kMaxLanes) throw CudaFail{cudaErrorInvalidDevice, "device index", __LINE__};
+  Ctx& c = g_ctx[dev * kMaxLanes + lane];
   if (c.ready) return c;
   std::lock_guard<std::mutex> g(g_init_mu);
   if (c.ready) return c;
@@ -98,6 +107,7 @@ Ctx& get_ctx(int dev) {
   c.pinned_cap = 4 << 20;
   CU(cudaMallocHost(reinterpret_cast<void**>(&c.pinned), c.pinned_cap));
   c.dev = dev;
+  c.shared = &g_shared[dev];
   c.ready = true;
   return c;
 }
@@ -418,10 +428,12 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
   if (in.cols) {
     PrepArgs pa;
     pa.d = d; pa.n = n; pa.flags = nonfinite_flag;
+    std::lock_guard<std::mutex> cache_guard(s.c.shared->mu);
+    auto& cache = s.c.shared->cache;
     for (int t = 0; t < d; ++t) {
       const eb2_col_t& c = in.cols[t];
-      auto it = s.c.cache.find(c.key);
-      if (it == s.c.cache.end()) throw CudaFail{cudaErrorInvalidValue, "column key not in the device cache", __LINE__};
+      auto it = cache.find(c.key);
+      if (it == cache.end()) throw CudaFail{cudaErrorInvalidValue, "column key not in the device cache", __LINE__};
       const int64_t last = c.off + (n - 1) * c.stride;
       if (c.off < 0 || last < 0 || c.off >= it->second.second || last >= it->second.second)
         throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
@@ -429,8 +441,8 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
       pc.src = it->second.first; pc.off = c.off; pc.stride = c.stride; pc.mean = c.mean; pc.std = c.std;
       pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride;
       if (c.nkey != 0) {
-        auto nt = s.c.cache.find(c.nkey);
-        if (nt == s.c.cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
+        auto nt = cache.find(c.nkey);
+        if (nt == cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
         const int64_t nlast = c.noff + (n - 1) * c.nstride;
         if (c.noff < 0 || nlast < 0 || nlast >= nt->second.second)
           throw CudaFail{cudaErrorInvalidValue, "noise slice outside the cached vector", __LINE__};
@@ -630,14 +642,17 @@ int eb2_init(void) {
 
 int eb2_shutdown(void) {
   std::lock_guard<std::mutex> g(g_init_mu);
-  for (int d = 0; d < kMaxDev; ++d) {
+  for (int d = 0; d < kMaxDev * kMaxLanes; ++d) {
     Ctx& c = g_ctx[d];
     if (!c.ready) continue;
     std::lock_guard<std::mutex> g2(c.mu);
     cudaSetDevice(c.dev);
     cudaStreamSynchronize(c.stream);
-    for (auto& kv : c.cache) cudaFreeAsync(kv.second.first, c.stream);
-    c.cache.clear();
+    {
+      std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+      for (auto& kv : c.shared->cache) cudaFreeAsync(kv.second.first, c.stream);
+      c.shared->cache.clear();
+    }
     cudaStreamSynchronize(c.stream);
     for (auto& e : c.ev) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
@@ -649,9 +664,12 @@ int eb2_shutdown(void) {
 }
 
 int eb2_last_timing(int dev, double* ms, int* launches) {
-  if (dev < 0 || dev >= kMaxDev || !g_ctx[dev].ready) return fail(EB2_ERR_ARG, "device %d has no context", dev);
-  if (ms) for (int i = 0; i < 5; ++i) ms[i] = g_ctx[dev].last_ms[i];
-  if (launches) *launches = g_ctx[dev].last_launches;
+  const int ord = dev & 0xff, lane = (dev >> 8) & 0xff;
+  if (dev < 0 || ord >= kMaxDev || lane >= kMaxLanes || !g_ctx[ord * kMaxLanes + lane].ready)
+    return fail(EB2_ERR_ARG, "device %d has no context", dev);
+  const Ctx& c = g_ctx[ord * kMaxLanes + lane];
+  if (ms) for (int i = 0; i < 5; ++i) ms[i] = c.last_ms[i];
+  if (launches) *launches = c.last_launches;
   return EB2_OK;
 }
 
@@ -660,17 +678,18 @@ int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
   if (key == 0 || !host || n <= 0) return fail(EB2_ERR_ARG, "eb2_cache_put: bad argument");
   return guarded(dev, [&](Ctx& c) {
     CU(cudaSetDevice(c.dev));
-    auto it = c.cache.find(key);
-    if (it != c.cache.end()) {
-      CU(cudaFreeAsync(it->second.first, c.stream));
-      c.cache.erase(it);
-    }
     double* p = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(double) * n, c.stream));   // from the cached pool
     cudaError_t e = cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);     // the caller may reuse `host` right away
     if (e != cudaSuccess) { cudaFreeAsync(p, c.stream); throw CudaFail{e, "eb2_cache_put copy", __LINE__}; }
-    c.cache[key] = {p, n};
+    std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+    auto it = c.shared->cache.find(key);
+    if (it != c.shared->cache.end()) {
+      cudaFreeAsync(it->second.first, c.stream);
+      c.shared->cache.erase(it);
+    }
+    c.shared->cache[key] = {p, n};
     return EB2_OK;
   });
 }
@@ -678,12 +697,14 @@ int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
 int eb2_cache_drop(int dev, uint64_t key) {
   return guarded(dev, [&](Ctx& c) {
     CU(cudaSetDevice(c.dev));
+    std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+    auto& cache = c.shared->cache;
     if (key == 0) {
-      for (auto& kv : c.cache) cudaFreeAsync(kv.second.first, c.stream);
-      c.cache.clear();
+      for (auto& kv : cache) cudaFreeAsync(kv.second.first, c.stream);
+      cache.clear();
     } else {
-      auto it = c.cache.find(key);
-      if (it != c.cache.end()) { cudaFreeAsync(it->second.first, c.stream); c.cache.erase(it); }
+      auto it = cache.find(key);
+      if (it != cache.end()) { cudaFreeAsync(it->second.first, c.stream); cache.erase(it); }
     }
     return EB2_OK;
   });

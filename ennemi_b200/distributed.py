@@ -85,7 +85,7 @@ def _all_reduce_sum(block: np.ndarray, group=None) -> np.ndarray:
     backend = dist.get_backend(group)
     t = torch.from_numpy(np.ascontiguousarray(block, dtype=np.float64))
     if backend == "nccl":
-        dev = torch.device("cuda", _devices.current())
+        dev = torch.device("cuda", _devices.ordinal(_devices.current()))
         t = t.to(dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return t.cpu().numpy()
@@ -150,7 +150,7 @@ def fan_out(func: Callable, params: Sequence, callback: Optional[Callable[[int],
     backend = dist.get_backend(group)
     t = torch.from_numpy(local)
     if backend == "nccl":
-        t = t.to(torch.device("cuda", _devices.current()))
+        t = t.to(torch.device("cuda", _devices.ordinal(_devices.current())))
     gathered = [torch.empty_like(t) for _ in range(size)]
     dist.all_gather(gathered, t, group=group)
     table = np.stack([g.cpu().numpy() for g in gathered])          # [rank][slot]

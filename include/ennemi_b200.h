@@ -21,8 +21,11 @@
  *  - return value: 0 on success, an EB2_ERR_* code otherwise; eb2_last_error() gives the
  *    thread-local message.  There is no CPU fallback: without a usable CUDA device every
  *    estimator returns EB2_ERR_CUDA.
- *  - thread safety: all entry points may be called concurrently; calls on the same `dev`
- *    serialise on that device's stream and workspace.
+ *  - `dev` = CUDA device ordinal in bits 0-7, optionally a stream "lane" (0..3) in bits 8-15:
+ *    each (device, lane) has its own stream, events and staging buffers, so small independent
+ *    tasks issued from different host threads run concurrently on one GPU.
+ *  - thread safety: all entry points may be called concurrently; calls on the same (device, lane)
+ *    serialise on that lane's stream and workspace.
  */
 #ifndef ENNEMI_B200_H
 #define ENNEMI_B200_H
