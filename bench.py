@@ -239,6 +239,32 @@ def run_gpu(args):
         fan = {"value": world * 1e3 / (ms_f / args.steps), "unit": UNIT, "scaling": "weak", "ms_per_step": ms_f / args.steps,
                "note": "independent (pair / lag) tasks fanned out: one full N=1e6 estimate per rank per step, no collective"}
 
+    # second half of BASELINE.json's metric: pairwise_mi wall time, 64 variables x N = 100,000 (configs[3]),
+    # through the public API on host arrays; with N > 1 the 2,016 pair tasks are dealt over the ranks
+    pairwise = None
+    if not args.no_pairwise:
+        ebd.enable_row_sharding(False)
+        ebd.enable_task_fanout(world > 1)
+        data = np.random.default_rng(0).normal(size=(100_000, 64))
+        eb.pairwise_mi(data[:, :8], k=K_NEIGH)                                   # warm-up (28 pairs)
+        barrier()
+        t0 = time.perf_counter()
+        pw = eb.pairwise_mi(data, k=K_NEIGH)
+        barrier()
+        pw_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([pw_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pw_s = float(t.item())
+        pairwise = {"metric": "pairwise_mi wall time, 64 vars", "value": pw_s, "unit": "s", "higher_is_better": False,
+                    "pairs": 2016, "n": 100_000, "k": K_NEIGH, "scaling": "strong",
+                    "max_offdiag_mi": float(np.nanmax(pw)),
+                    "note": "ennemi_b200.pairwise_mi(data, k=3) on a host (100000, 64) array: columns cached on the "
+                            "GPU once, per-pair rescaling on the device, pair tasks on 3 stream lanes per GPU"
+                            + (", tasks dealt over the ranks + one all_gather" if world > 1 else "")}
+        ebd.enable_task_fanout(False)
+        ebd.enable_row_sharding(True)
+
     brute = None
     if world == 1 and not args.no_brute:
         bsteps = max(2, min(args.steps, 3))
@@ -280,6 +306,8 @@ def run_gpu(args):
     }
     if fan:
         line["fanout"] = fan
+    if pairwise:
+        line["pairwise"] = pairwise
     if brute:
         b_ms, b_knn, b_pairs, b_val = brute
         b_ops = float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR
@@ -303,6 +331,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-brute", action="store_true", help="skip the brute-force (EB2_FLAG_NO_PRUNE) leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-pairwise", action="store_true", help="skip the pairwise_mi (64 variables) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -32,8 +32,15 @@ def run_tasks(func: Callable[[T], float], params: Sequence[T], max_threads: Opti
               time_estimate: float, callback: Callable[[int], None]) -> List[float]:
     from . import distributed
     if distributed.task_fanout_enabled():
-        # one process per GPU: deal the tasks over the ranks, gather the scalars
-        return distributed.fan_out(func, params, callback)
+        # one process per GPU: deal the tasks over the ranks, run this rank's share on its own GPU
+        # (threads + stream lanes as below), then all-gather the scalars
+        return distributed.fan_out(func, params, callback,
+                                   runner=lambda f, p, cb: _run_local(f, p, max_threads, time_estimate, cb))
+    return _run_local(func, params, max_threads, time_estimate, callback)
+
+
+def _run_local(func: Callable[[T], float], params: Sequence[T], max_threads: Optional[int],
+               time_estimate: float, callback: Callable[[int], None]) -> List[float]:
     devices = _devices.visible()
     workers = max(1, len(devices)) * WORKERS_PER_DEVICE
     if len(params) * time_estimate < INLINE_BUDGET_S:

@@ -133,16 +133,27 @@ def sharded_entropy(coords, k: int = 3, flags: int = 0, group=None) -> float:
 
 
 def fan_out(func: Callable, params: Sequence, callback: Optional[Callable[[int], None]] = None,
-            group=None) -> List[float]:
+            group=None, runner: Optional[Callable] = None) -> List[float]:
     """Runs ``func(params[i])`` for the tasks ``i = rank, rank + world, ...`` on this rank and returns
-    the full task-ordered result list on every rank (one all_gather of fp64 scalars)."""
+    the full task-ordered result list on every rank (one all_gather of fp64 scalars).  ``runner(func,
+    params, callback)`` executes this rank's share (default: sequentially)."""
     rank, size = world()
     mine = list(range(rank, len(params), size))
-    local = np.full(len(range(0, len(params), size)) if size else 0, np.nan)
-    for slot, i in enumerate(mine):
-        local[slot] = func(params[i])
+    slots = len(range(0, len(params), size)) if size else 0
+    local = np.full(slots, np.nan)
+
+    def local_cb(slot: int) -> None:
         if callback is not None:
-            callback(i)
+            callback(mine[slot])
+
+    if runner is None:
+        values = []
+        for slot, i in enumerate(mine):
+            values.append(func(params[i]))
+            local_cb(slot)
+    else:
+        values = runner(func, [params[i] for i in mine], local_cb)
+    local[:len(mine)] = values
     if size == 1:
         return [float(v) for v in local[:len(params)]]
     import torch
