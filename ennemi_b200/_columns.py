@@ -154,8 +154,9 @@ class ColsTask:
         self.lag, self.hi, self.lo, self.cond_lag, self.k, self.preprocess = lag, hi, lo, cond_lag, k, preprocess
         self.n_total = len(yview)
 
-    def run(self) -> float:
-        dev = _devices.current()
+    def describe(self, dev: int):
+        """(descriptors, n) of this task for device ``dev``: uploads what is missing, computes (cached)
+        window statistics, raises the reference's errors for impossible windows."""
         lo_pad, hi_pad = max(self.hi, 0), min(self.lo, 0)            # as _align.lagged_windows
         n_tot = self.n_total
         xs = self.xview[lo_pad - self.lag: n_tot - self.lag + hi_pad]   # views: non-integer lags raise here
@@ -214,6 +215,11 @@ class ColsTask:
                     descs.append(_native.ColDesc(key, off, 1, 0.0, 0.0, 0, 0, 1))
                 else:
                     descs.append(_native.ColDesc(key, off, 1, float(zmean[j]), float(zstd[j]), nkey, j, c))
+        return descs, n
+
+    def run(self) -> float:
+        dev = _devices.current()
+        descs, n = self.describe(dev)
         try:
             if self.zkeys:
                 return _native.cmi_cols(descs, n, self.k, dev=dev)
@@ -222,3 +228,23 @@ class ColsTask:
             if e.nan:
                 raise ValueError(_checks.MSG_NANS_LEFT) from None
             raise ValueError(str(e)) from None
+
+
+BATCH = 8     # tasks per native call: one interpreter round trip (and one GIL release) per batch
+
+
+def run_batch(tasks: List["ColsTask"]) -> List[float]:
+    """Estimates a run of same-shaped column tasks with one call into the library."""
+    dev = _devices.current()
+    described = [t.describe(dev) for t in tasks]
+    n = described[0][1]
+    values, status = _native.mi_cols_batch([d for d, _ in described], n, tasks[0].k, dev=dev)
+    for st in status:
+        if st:
+            code, data_flags = int(st) & 0xFF, int(st) >> 8
+            if code == _native.ERR_NONFINITE:
+                if data_flags & 1:
+                    raise ValueError(_checks.MSG_NANS_LEFT)
+                raise ValueError("data must be finite, check for nan or inf values")
+            raise RuntimeError(f"ennemi_b200: batched estimate failed with code {code}")
+    return [float(v) for v in values]

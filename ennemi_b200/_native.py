@@ -32,6 +32,7 @@ EXPORTS = (
     "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
+    "eb2_mi_cols_batch",
 )
 
 _lib = None
@@ -89,6 +90,7 @@ def load():
         lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
+        lib.eb2_mi_cols_batch.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _i64, _int, _u32, _c_dp, ctypes.POINTER(_int)]
         for name in EXPORTS:
             getattr(lib, name)
         _lib = lib
@@ -359,3 +361,17 @@ def ksg_mi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
 def cmi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
     """Frenzel-Pompe CMI of cached device columns (``cols``: x, y, then the condition's columns)."""
     return _cols_call(load().eb2_cmi_cols, cols, dev, n, len(cols) - 2, k, flags)
+
+
+def mi_cols_batch(tasks, n: int, k: int, dev: int = 0, flags: int = 0):
+    """``tasks``: list of descriptor lists of equal length (2 + c).  Returns (values, status) arrays;
+    ``status[t]`` is 0 or ``err | data_flags << 8``."""
+    lib = load()
+    d = len(tasks[0])
+    flat = (ColDesc * (len(tasks) * d))(*[c for t in tasks for c in t])
+    values = np.empty(len(tasks))
+    status = (ctypes.c_int * len(tasks))()
+    rc = lib.eb2_mi_cols_batch(dev, flat, len(tasks), d - 2, n, k, flags, values.ctypes.data_as(_c_dp), status)
+    if rc:
+        _raise(rc)
+    return values, np.frombuffer(status, dtype=np.int32).copy()

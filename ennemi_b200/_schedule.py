@@ -41,6 +41,9 @@ def run_tasks(func: Callable[[T], float], params: Sequence[T], max_threads: Opti
 
 def _run_local(func: Callable[[T], float], params: Sequence[T], max_threads: Optional[int],
                time_estimate: float, callback: Callable[[int], None]) -> List[float]:
+    from . import _columns
+    if len(params) > 1 and all(isinstance(p, _columns.ColsTask) for p in params):
+        return _run_column_batches(list(params), max_threads, time_estimate, callback)
     devices = _devices.visible()
     workers = max(1, len(devices)) * WORKERS_PER_DEVICE
     if len(params) * time_estimate < INLINE_BUDGET_S:
@@ -70,4 +73,40 @@ def _run_local(func: Callable[[T], float], params: Sequence[T], max_threads: Opt
         concurrent.futures.wait(futures)
         for f in futures:
             f.result()          # re-raise the first failure, like the reference's done-callback does
+    return results
+
+
+def _run_column_batches(tasks, max_threads: Optional[int], time_estimate: float,
+                        callback: Callable[[int], None]) -> List[float]:
+    """Column tasks (device-resident variables) go to the library in batches: consecutive batches
+    rotate over the (GPU, lane) workers, one native call per batch."""
+    from . import _columns
+    devices = _devices.visible()
+    workers = max(1, len(devices)) * WORKERS_PER_DEVICE
+    if len(tasks) * time_estimate < INLINE_BUDGET_S:
+        workers = 1
+    if max_threads is not None:
+        workers = min(workers, max_threads)
+    size = max(1, min(_columns.BATCH, -(-len(tasks) // max(workers, 1))))
+    batches = [list(range(lo, min(lo + size, len(tasks)))) for lo in range(0, len(tasks), size)]
+    workers = max(1, min(workers, len(batches)))
+    results: List[float] = [float("nan")] * len(tasks)
+
+    def work(b: int, dev: int) -> None:
+        with _devices.use(dev):
+            values = _columns.run_batch([tasks[i] for i in batches[b]])
+        for i, v in zip(batches[b], values):
+            results[i] = v
+            callback(i)
+
+    if workers <= 1:
+        for b in range(len(batches)):
+            work(b, _devices.current())
+        return results
+    with concurrent.futures.ThreadPoolExecutor(workers, "ennemi-b200-work") as pool:
+        futures = [pool.submit(work, b, _devices.with_lane(devices[b % len(devices)], (b // len(devices)) % _devices.LANES))
+                   for b in range(len(batches))]
+        concurrent.futures.wait(futures)
+        for f in futures:
+            f.result()
     return results

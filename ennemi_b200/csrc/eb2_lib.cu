@@ -712,6 +712,23 @@ int eb2_cache_drop(int dev, uint64_t key) {
 
 int eb2_last_data_flags(void) { return g_data_flags; }
 
+// Many tasks of one shape in one call: no interpreter work and no GIL between tasks.  Task t uses
+// cols[t * d .. t * d + d).  status[t] = 0, or EB2_ERR_* | data_flags << 8 with values[t] = NaN; the
+// call itself fails only on bad arguments.
+int eb2_mi_cols_batch(int dev, const eb2_col_t* cols, int64_t ntasks, int c_dim, int64_t n, int k, uint32_t flags,
+                      double* values, int* status) {
+  if (!cols || !values || !status || ntasks < 0 || c_dim < 0) return fail(EB2_ERR_ARG, "eb2_mi_cols_batch: bad argument");
+  const int d = 2 + c_dim;
+  for (int64_t t = 0; t < ntasks; ++t) {
+    g_data_flags = 0;
+    const int rc = c_dim == 0 ? eb2_ksg_mi_cols(dev, cols + t * d, n, k, flags, values + t)
+                              : eb2_cmi_cols(dev, cols + t * d, n, c_dim, k, flags, values + t);
+    status[t] = rc ? (rc | (g_data_flags << 8)) : 0;
+    if (rc) values[t] = std::numeric_limits<double>::quiet_NaN();
+  }
+  return EB2_OK;
+}
+
 // ---- a1: KSG ------------------------------------------------------------------------------------
 static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
                          double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {

@@ -154,6 +154,10 @@ typedef struct eb2_col {
 EB2_API int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value);
 EB2_API int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c, int k, uint32_t flags, double* value);
 EB2_API int eb2_last_data_flags(void);
+/* ntasks tasks of one shape (c = 0: a1, c > 0: a2) in one call; task t uses cols[t*(2+c) .. ).  status[t] is 0
+ * or EB2_ERR_* | data_flags << 8 (values[t] = NaN).  Replaces a host loop of per-task calls. */
+EB2_API int eb2_mi_cols_batch(int dev, const eb2_col_t* cols, int64_t ntasks, int c, int64_t n, int k, uint32_t flags,
+                              double* values, int* status);
 
 /* roofline denominator: FP64 (DADD) instructions per second this device retires, in 10^12/s,
  * measured with a register-resident kernel (best of 5).  The all-pairs kernels are bound by it. */

@@ -40,7 +40,7 @@ class OracleBackend:
     signatures, answers computed by the CPU oracle.  Never used by the product."""
 
     PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
-               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols")
+               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch")
 
     def __init__(self, backend="scipy"):
         import oracle
@@ -107,6 +107,16 @@ class OracleBackend:
     def ksg_mi_cols(self, descs, n, k, dev=0, flags=0):
         x, y = self._gather(descs, n, dev)
         return self.o.ksg_mi(x, y, k, backend=self.backend)["value"]
+
+    def mi_cols_batch(self, tasks, n, k, dev=0, flags=0):
+        from ennemi_b200 import _native
+        values, status = np.full(len(tasks), np.nan), np.zeros(len(tasks), dtype=np.int32)
+        for t, descs in enumerate(tasks):
+            try:
+                values[t] = self.ksg_mi_cols(descs, n, k, dev) if len(descs) == 2 else self.cmi_cols(descs, n, k, dev)
+            except _native.NonFiniteInput as e:
+                status[t] = _native.ERR_NONFINITE | ((1 if e.nan else 2) << 8)
+        return values, status
 
     def cmi_cols(self, descs, n, k, dev=0, flags=0):
         rows = self._gather(descs, n, dev)
