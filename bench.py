@@ -38,7 +38,7 @@ N_ROWS = 1_000_000
 K_NEIGH = 3
 RHO = 0.6
 FP64_OPS_PER_PAIR = 4          # 2-D space: 2 subtractions + 2 compares (2d per pair)
-SAMPLE_STRIDE = 20             # CPU baseline: every 20th row is queried, trees hold all rows
+SAMPLE_STRIDE = 50             # CPU baseline: every 50th row is queried, trees hold all rows
 # dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel<2,4> at this workload, one ncu --set full capture
 # (profiles/ncu_r01_summary.md): the 16 MB point set is read once, everything else stays in the 126 MB L2
 NCU_DRAM_BYTES_PER_LAUNCH = 16.4e6

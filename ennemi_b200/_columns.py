@@ -107,6 +107,11 @@ class ColumnStore:
                 _native.cache_put(key, self._cols[key], dev=dev)
                 have.add(key)
 
+    def missing(self, dev: int, *keys) -> bool:
+        with self._lock:
+            have = self._on_device.get(_devices.ordinal(dev), set())
+            return any(k not in have for k in keys)
+
     def stats(self, tag: tuple, compute):
         with self._lock:
             hit = self._stats.get(tag)
@@ -189,6 +194,17 @@ class ColsTask:
                     std = 0.0
             return _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
 
+        if n >= OVERLAP_MIN_ROWS and self.preprocess and self.store.missing(dev, self.xkey, self.ykey):
+            # large first-time windows: x's upload overlaps y's statistics and vice versa (both release the GIL)
+            def side(key, off, view, upload_first):
+                if upload_first:
+                    self.store.ensure(dev, key)
+                self.store.stats((key, off, n), lambda: window_stats(view))
+                if not upload_first:
+                    self.store.ensure(dev, key)
+            fut = _helper_pool().submit(side, self.ykey, y_off, ys, False)     # y: statistics, then upload
+            side(self.xkey, x_off, xs, True)                                   # x: upload, then statistics
+            fut.result()
         descs.append(one(self.xkey, x_off, xs, (self.xkey, x_off, n)))
         descs.append(one(self.ykey, y_off, ys, (self.ykey, y_off, n)))
         if self.zkeys:
@@ -221,6 +237,15 @@ class ColsTask:
         dev = _devices.current()
         descs, n = self.describe(dev)
         try:
+            from . import distributed
+            if distributed.row_sharding_enabled():
+                # one process per GPU, every rank holds the columns: shard the query rows, one all-reduce
+                rank, size = distributed.world()
+                lo, hi = distributed.shard_bounds(n, rank, size)
+                part = distributed._all_reduce_sum(_native.mi_cols_rows(descs, n, self.k, lo, hi, dev=dev))
+                if self.zkeys:
+                    return _native.cmi_finish(part, n, self.k)
+                return _native.ksg_mi_finish(part, n, self.k)
             if self.zkeys:
                 return _native.cmi_cols(descs, n, self.k, dev=dev)
             return _native.ksg_mi_cols(descs, n, self.k, dev=dev)
@@ -228,6 +253,20 @@ class ColsTask:
             if e.nan:
                 raise ValueError(_checks.MSG_NANS_LEFT) from None
             raise ValueError(str(e)) from None
+
+
+OVERLAP_MIN_ROWS = 200_000
+_pool = None
+_pool_lock = threading.Lock()
+
+
+def _helper_pool():
+    global _pool
+    with _pool_lock:
+        if _pool is None:
+            import concurrent.futures
+            _pool = concurrent.futures.ThreadPoolExecutor(2, "ennemi-b200-prep")
+        return _pool
 
 
 BATCH = 8     # tasks per native call: one interpreter round trip (and one GIL release) per batch

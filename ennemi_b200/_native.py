@@ -32,7 +32,7 @@ EXPORTS = (
     "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
-    "eb2_mi_cols_batch",
+    "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows",
 )
 
 _lib = None
@@ -90,6 +90,8 @@ def load():
         lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
+        lib.eb2_ksg_mi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _i64, _i64, _c_dp]
+        lib.eb2_cmi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _i64, _i64, _c_dp]
         lib.eb2_mi_cols_batch.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _i64, _int, _u32, _c_dp, ctypes.POINTER(_int)]
         for name in EXPORTS:
             getattr(lib, name)
@@ -375,3 +377,20 @@ def mi_cols_batch(tasks, n: int, k: int, dev: int = 0, flags: int = 0):
     if rc:
         _raise(rc)
     return values, np.frombuffer(status, dtype=np.int32).copy()
+
+
+def mi_cols_rows(cols, n: int, k: int, row_lo: int, row_hi: int, dev: int = 0, flags: int = 0) -> np.ndarray:
+    """Partial block of a KSG (2 columns) or CMI (2 + c columns) estimate on cached columns for the
+    query rows [row_lo, row_hi)."""
+    lib = load()
+    arr = (ColDesc * len(cols))(*cols)
+    partial = np.zeros(P_LEN)
+    if len(cols) == 2:
+        rc = lib.eb2_ksg_mi_cols_rows(dev, arr, n, k, flags, row_lo, row_hi, partial.ctypes.data_as(_c_dp))
+    else:
+        rc = lib.eb2_cmi_cols_rows(dev, arr, n, len(cols) - 2, k, flags, row_lo, row_hi, partial.ctypes.data_as(_c_dp))
+    if rc == ERR_NONFINITE:
+        raise NonFiniteInput(lib.eb2_last_error().decode(), bool(lib.eb2_last_data_flags() & 1))
+    if rc:
+        _raise(rc)
+    return partial

@@ -42,7 +42,8 @@ def run_tasks(func: Callable[[T], float], params: Sequence[T], max_threads: Opti
 def _run_local(func: Callable[[T], float], params: Sequence[T], max_threads: Optional[int],
                time_estimate: float, callback: Callable[[int], None]) -> List[float]:
     from . import _columns
-    if len(params) > 1 and all(isinstance(p, _columns.ColsTask) for p in params):
+    from . import distributed as _dist
+    if len(params) > 1 and not _dist.row_sharding_enabled() and all(isinstance(p, _columns.ColsTask) for p in params):
         return _run_column_batches(list(params), max_threads, time_estimate, callback)
     devices = _devices.visible()
     workers = max(1, len(devices)) * WORKERS_PER_DEVICE
@@ -51,6 +52,8 @@ def _run_local(func: Callable[[T], float], params: Sequence[T], max_threads: Opt
     if max_threads is not None:
         workers = min(workers, max_threads)
     workers = min(workers, max(len(params), 1))
+    if _dist.row_sharding_enabled():
+        workers = 1          # every estimate is a collective: all ranks must run the tasks in the same order
 
     if workers <= 1:
         out = []

@@ -135,8 +135,7 @@ DEVICE_COLUMNS_MIN_ROWS = int(os.environ.get("ENNEMI_B200_COLUMNS_MIN_ROWS", "20
 
 def _device_store(arrays, mask, drop_nan: bool, any_discrete: bool):
     """A :class:`_columns.ColumnStore` when the call qualifies for device-resident columns, else None."""
-    from . import distributed
-    if arrays[0].shape[0] < DEVICE_COLUMNS_MIN_ROWS or distributed.row_sharding_enabled():
+    if arrays[0].shape[0] < DEVICE_COLUMNS_MIN_ROWS:
         return None
     if not _columns.eligible(arrays, mask, drop_nan, any_discrete):
         return None

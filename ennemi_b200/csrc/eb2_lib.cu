@@ -190,6 +190,7 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   ps.sort_row = sort_row;
   // 512-row tiles only when they still give every SM several CTAs; smaller sets use 256-row tiles
   ps.qpt = (n / tile_rows(kMaxQpt) >= 4 * static_cast<int64_t>(s.c.sm_count)) ? kMaxQpt : 1;
+  if (const char* e = getenv("EB2_QPT")) ps.qpt = atoi(e) == 1 ? 1 : 2;   // tuning knob
   const int nseg = cls ? static_cast<int>(class_size.size()) : 1;
   std::vector<int> seg_rank(nseg);
   ps.seg_slot.resize(nseg);
@@ -779,6 +780,14 @@ int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t fl
   return ksg_rows_impl(dev, in, n, k, row_lo, row_hi, partial, eps_out, nx_out, ny_out);
 }
 
+int eb2_ksg_mi_cols_rows(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, int64_t row_lo,
+                         int64_t row_hi, double* partial) {
+  if (!cols || !partial) return fail(EB2_ERR_ARG, "cols/partial is NULL");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2, k)) return rc0;
+  Input in; in.cols = cols; in.flags = flags & ~EB2_FLAG_DEVICE_INPUT;
+  return ksg_rows_impl(dev, in, n, k, row_lo, row_hi, partial, nullptr, nullptr, nullptr);
+}
+
 int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value) {
   if (!cols || !value) return fail(EB2_ERR_ARG, "cols/value is NULL");
   if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2, k)) return rc0;
@@ -847,6 +856,15 @@ int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uin
   if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
   Input in; in.coords = coords; in.flags = flags;
   return cmi_rows_impl(dev, in, n, c_dim, k, row_lo, row_hi, partial, eps_out, nxz_out, nyz_out, nz_out);
+}
+
+int eb2_cmi_cols_rows(int dev, const eb2_col_t* cols, int64_t n, int c_dim, int k, uint32_t flags, int64_t row_lo,
+                      int64_t row_hi, double* partial) {
+  if (!cols || !partial) return fail(EB2_ERR_ARG, "cols/partial is NULL");
+  if (c_dim < 1) return fail(EB2_ERR_ARG, "condition needs at least one dimension");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2 + c_dim, k)) return rc0;
+  Input in; in.cols = cols; in.flags = flags & ~EB2_FLAG_DEVICE_INPUT;
+  return cmi_rows_impl(dev, in, n, c_dim, k, row_lo, row_hi, partial, nullptr, nullptr, nullptr, nullptr);
 }
 
 int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c_dim, int k, uint32_t flags, double* value) {

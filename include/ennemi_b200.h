@@ -153,6 +153,11 @@ typedef struct eb2_col {
  * eb2_last_data_flags() tells NaN input (bit0) from otherwise non-finite prepared data (bit1). */
 EB2_API int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value);
 EB2_API int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c, int k, uint32_t flags, double* value);
+/* ... and with query rows sharded (partial block as in eb2_*_rows; finish with eb2_*_finish) */
+EB2_API int eb2_ksg_mi_cols_rows(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags,
+                                 int64_t row_lo, int64_t row_hi, double* partial);
+EB2_API int eb2_cmi_cols_rows(int dev, const eb2_col_t* cols, int64_t n, int c, int k, uint32_t flags,
+                              int64_t row_lo, int64_t row_hi, double* partial);
 EB2_API int eb2_last_data_flags(void);
 /* ntasks tasks of one shape (c = 0: a1, c > 0: a2) in one call; task t uses cols[t*(2+c) .. ).  status[t] is 0
  * or EB2_ERR_* | data_flags << 8 (values[t] = NaN).  Replaces a host loop of per-task calls. */
