@@ -55,6 +55,10 @@ struct KnnArgs {
   const Tile* tiles;
   int k;                 // result = (k+1)-th smallest, i.e. best[k]
   int sort_row;          // row of P sorted ascending inside every segment (enables pruning), or -1
+  // two-level layout ("cells", single-segment sets, D >= 2): the set is ordered by sort_row ACROSS chunks of
+  // chunk_len(D) slots and by rows.row[1] INSIDE each chunk; cell_lo/cell_hi = range of sort_row per chunk
+  const double* cell_lo;
+  const double* cell_hi;
   double* eps;           // out, per query slot
   double* heap;          // scratch for the large-k variant: [k+1][gridDim.x * tile_rows(QPT)]
   unsigned long long* pairs;  // work counter (pairs evaluated)
@@ -133,6 +137,25 @@ struct HeapRef {
   }
 };
 
+// first slot in [0, len) of the ascending array `a` whose value is >= v (NaN padding excluded by len)
+__device__ __forceinline__ int lower_bound_ge(const double* a, int len, double v) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// first slot whose value is > v
+__device__ __forceinline__ int upper_bound_gt(const double* a, int len, double v) {
+  int lo = 0, hi = len;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // ---- in-CTA reordering of the tile's queries -------------------------------------------------------
 // Bitonic sort of the kTileQ per-query keys (ascending) in shared memory; afterwards rank r holds the
 // home index sidx[r] of the query with the r-th smallest key.  Used to make warps homogeneous in
@@ -168,6 +191,46 @@ __device__ __forceinline__ void cta_permute(double* xch, const int (&src)[QPT], 
   __syncthreads();
 }
 
+// ---- two-level layout: order the slots of every chunk by a second coordinate -----------------------
+// The point set arrives ordered by `row1` globally.  Each CTA takes one chunk of TC slots, records the
+// range of row1 in it (cell_lo / cell_hi) and reorders the chunk's slots by `row2` (bitonic sort in
+// shared memory); all d rows and slot_row are permuted alike.  NaN padding sorts last.
+template <int TC>
+__global__ void __launch_bounds__(kThreads) cell_sort_kernel(double* P, int64_t stride, int d, int* slot_row, int64_t n,
+                                                            int row1, int row2, double* cell_lo, double* cell_hi) {
+  __shared__ __align__(16) double skey[TC];
+  __shared__ int sidx[TC];
+  __shared__ __align__(16) double sval[TC];
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * TC;
+  const int nvalid = (int)min((int64_t)TC, n - base);
+  if (tid == 0) {
+    cell_lo[blockIdx.x] = P[row1 * stride + base];
+    cell_hi[blockIdx.x] = P[row1 * stride + base + nvalid - 1];
+  }
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  for (int i = tid; i < TC; i += kThreads) {
+    const double v = (i < nvalid) ? P[row2 * stride + base + i] : kInf;   // padding sorts last
+    skey[i] = (v == v) ? v : kInf;
+    sidx[i] = i;
+  }
+  __syncthreads();
+  cta_sort_keys<TC>(skey, sidx);
+  // slots past nvalid are padding (NaN / -1) and stay padding; the row may end before base + TC
+  const int nslots = (int)min((int64_t)TC, stride - base);
+  const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  for (int t = 0; t < d; ++t) {
+    for (int i = tid; i < nvalid; i += kThreads) sval[i] = P[t * stride + base + i];
+    __syncthreads();
+    for (int i = tid; i < nslots; i += kThreads) P[t * stride + base + i] = (i < nvalid) ? sval[sidx[i]] : kNaN;
+    __syncthreads();
+  }
+  int* ival = reinterpret_cast<int*>(sval);
+  for (int i = tid; i < nvalid; i += kThreads) ival[i] = slot_row[base + i];
+  __syncthreads();
+  for (int i = tid; i < nslots; i += kThreads) slot_row[base + i] = (i < nvalid) ? ival[sidx[i]] : -1;
+}
+
 // candidates tested per branch in the all-pairs inner loops (register budget: 2*G*D for the group)
 __host__ __device__ constexpr int group_len(int d) { return d <= 2 ? 4 : 2; }
 // resident CTAs per SM the kernels are compiled for, from a register estimate:
@@ -179,12 +242,12 @@ __host__ __device__ constexpr int knn_min_blocks(int d, int k1t, int qpt) {
 
 // all queries of one thread against one staged candidate chunk (shared memory, broadcast LDS.128)
 template <int D, int K1T, int TC, int QPT>
-__device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int len, const double (&q)[QPT][D],
+__device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int lo, int hi, const double (&q)[QPT][D],
                                                double (&best)[QPT][(K1T > 0 ? K1T : 1)], double (&thr)[QPT],
                                                const HeapRef (&heap)[QPT]) {
   constexpr int kGroup = group_len(D);
 #pragma unroll 1
-  for (int jj = 0; jj < len; jj += kGroup) {
+  for (int jj = lo; jj < hi; jj += kGroup) {
     bool any = false;
     {
       double c[kGroup][D];
@@ -255,9 +318,11 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
     int rstart[QPT], lend[QPT];   // deferred remainder of the search (segment-relative slots)
     bool valid[QPT];
     HeapRef heap[QPT];
+    const bool cells = a.cell_lo != nullptr;
 #pragma unroll
     for (int i = 0; i < QPT; ++i) {
-      const int qi = tid + i * kThreads;
+      // cells: a warp owns 32*QPT CONSECUTIVE slots (consecutive in the in-chunk coordinate)
+      const int qi = cells ? QPT * tid + i : tid + i * kThreads;
       qslot[i] = qi;
       rstart[i] = tile.c_len;
       lend[i] = 0;
@@ -294,8 +359,129 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
       for (int j = 0; j < nchunks; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
+        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, 0, len, q, best, thr, heap);
         __syncthreads();   // everyone is done with sbuf before the next bulk copy lands in it
+      }
+    } else if (cells) {
+      if constexpr (D >= 2) {
+        // ---- two-level search: chunks pruned by coordinate 0 (CTA-wide), candidates inside a staged chunk
+        //      by coordinate 1 (per warp: its queries are consecutive in that coordinate, so a binary search
+        //      in shared memory gives the slot range that can matter).  All bounds are conservative w.r.t.
+        //      the rounded tests, the exact test decides: bit-exact.
+        constexpr int NH = (kTileQ / TC) > 0 ? (kTileQ / TC) : 1;     // home chunks of a tile
+        const int warp = tid >> 5;
+        const int home_lo = (tile.q_lo - tile.c_lo) / TC;
+        const int home_hi = (tile.q_lo - tile.c_lo + tile.q_n - 1) / TC;
+        const int own_lo = (tile.q_lo - tile.c_lo) + 32 * QPT * warp;            // segment-relative slots of this warp
+        const int own_hi = own_lo + 32 * QPT;
+        double ymin = kInf, ymax = -kInf;
+#pragma unroll
+        for (int i = 0; i < QPT; ++i)
+          if (valid[i]) { ymin = fmin(ymin, q[i][1]); ymax = fmax(ymax, q[i][1]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+          ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        const bool warp_has = ymin <= ymax;
+        // slot range [lo, hi) of the staged chunk j that can hold neighbours of this warp's queries
+        auto window = [&](int j, int len, int& lo, int& hi) {
+          double tmax = 0.0;
+#pragma unroll
+          for (int i = 0; i < QPT; ++i) tmax = fmax(tmax, valid[i] ? thr[i] : 0.0);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+          const double slack = 8.881784197001252e-16;  // 2^-50
+          const double lo_v = (ymin - tmax) - (fabs(ymin) + tmax) * slack;
+          const double hi_v = (ymax + tmax) + (fabs(ymax) + tmax) * slack;
+          const int lenv = min(TC, tile.c_len - j * TC);
+          const double* sy = sbuf + TC;                                      // row 1 of the staged chunk, ascending
+          lo = lower_bound_ge(sy, lenv, lo_v) & ~(kGroup - 1);
+          hi = min(len, (upper_bound_gt(sy, lenv, hi_v) + kGroup - 1) & ~(kGroup - 1));
+        };
+        int sa[NH], sb[NH];
+        // 1a. seed every list from the warp's own neighbourhood in its home chunk(s)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int j = home_lo + h;
+          sa[h] = sb[h] = 0;
+          if (j <= home_hi) {
+            const int len = fetch_chunk(j);
+            int aa = max(own_lo - 64, j * TC) - j * TC, bb = min(own_hi + 64, j * TC + len) - j * TC;
+            if (warp_has && aa < bb) {
+              aa &= ~(kGroup - 1);
+              bb = min(len, (bb + kGroup - 1) & ~(kGroup - 1));
+              sa[h] = aa; sb[h] = bb;
+              if ((tid & 31) == 0) npairs += (unsigned long long)(bb - aa) * 32 * QPT;
+              knn_scan_chunk<D, K1T, TC, QPT>(sbuf, aa, bb, q, best, thr, heap);
+            }
+            __syncthreads();
+          }
+        }
+        // 1b. the rest of the home chunk(s), windowed
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int j = home_lo + h;
+          if (j <= home_hi) {
+            const int len = fetch_chunk(j);
+            if (warp_has) {
+              int lo, hi;
+              window(j, len, lo, hi);
+              const int e1 = min(sa[h], hi), s2 = max(sb[h], lo);
+              if ((tid & 31) == 0) npairs += (unsigned long long)(max(0, e1 - lo) + max(0, hi - s2)) * 32 * QPT;
+              if (lo < e1) knn_scan_chunk<D, K1T, TC, QPT>(sbuf, lo, e1, q, best, thr, heap);
+              if (s2 < hi) knn_scan_chunk<D, K1T, TC, QPT>(sbuf, s2, hi, q, best, thr, heap);
+            }
+            __syncthreads();
+          }
+        }
+        // 2. outwards over the chunks
+        for (int j = home_hi + 1; j < nchunks; ++j) {
+          const double cmin = a.cell_lo[j];
+          bool need = false;
+#pragma unroll
+          for (int i = 0; i < QPT; ++i) need = need || (valid[i] && !((cmin - q[i][0]) >= thr[i]));
+          const bool wneed = __any_sync(0xffffffffu, need);
+          const int nneed = __syncthreads_count(need);
+          if (nneed == 0) break;
+          if (nneed < a.defer_below) {
+#pragma unroll
+            for (int i = 0; i < QPT; ++i)
+              if (valid[i] && !((cmin - q[i][0]) >= thr[i])) rstart[i] = j * TC;
+            break;
+          }
+          const int len = fetch_chunk(j);
+          if (wneed) {
+            int lo, hi;
+            window(j, len, lo, hi);
+            if ((tid & 31) == 0) npairs += (unsigned long long)max(0, hi - lo) * 32 * QPT;
+            if (lo < hi) knn_scan_chunk<D, K1T, TC, QPT>(sbuf, lo, hi, q, best, thr, heap);
+          }
+        }
+        __syncthreads();
+        for (int j = home_lo - 1; j >= 0; --j) {
+          const double cmax = a.cell_hi[j];
+          bool need = false;
+#pragma unroll
+          for (int i = 0; i < QPT; ++i) need = need || (valid[i] && !((q[i][0] - cmax) >= thr[i]));
+          const bool wneed = __any_sync(0xffffffffu, need);
+          const int nneed = __syncthreads_count(need);
+          if (nneed == 0) break;
+          if (nneed < a.defer_below) {
+#pragma unroll
+            for (int i = 0; i < QPT; ++i)
+              if (valid[i] && !((q[i][0] - cmax) >= thr[i])) lend[i] = min((j + 1) * TC, tile.c_len);
+            break;
+          }
+          const int len = fetch_chunk(j);
+          if (wneed) {
+            int lo, hi;
+            window(j, len, lo, hi);
+            if ((tid & 31) == 0) npairs += (unsigned long long)max(0, hi - lo) * 32 * QPT;
+            if (lo < hi) knn_scan_chunk<D, K1T, TC, QPT>(sbuf, lo, hi, q, best, thr, heap);
+          }
+        }
+        __syncthreads();
       }
     } else {
       // 1. the chunks that overlap the tile itself: seeds every list with near neighbours
@@ -304,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
       for (int j = home_lo; j <= home_hi; ++j) {
         const int len = fetch_chunk(j);
         if (tid == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * tile.q_n;
-        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
+        knn_scan_chunk<D, K1T, TC, QPT>(sbuf, 0, len, q, best, thr, heap);
         __syncthreads();
       }
       if (home_lo > 0 || home_hi + 1 < nchunks) {
@@ -372,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
           const int len = fetch_chunk(j);
           if (wneed) {
             if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * QPT;
-            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
+            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, 0, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -393,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
           const int len = fetch_chunk(j);
           if (wneed) {
             if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - j * TC) * 32 * QPT;
-            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, len, q, best, thr, heap);
+            knn_scan_chunk<D, K1T, TC, QPT>(sbuf, 0, len, q, best, thr, heap);
           }
         }
         __syncthreads();
@@ -503,9 +689,23 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
     const double q0 = q[0];
     // candidates that can still enter: gap in the sorted coordinate below the gate (monotone => exact)
     int lo = le.rstart, hi = le.rstart;
-    if (le.rstart < le.c_len) hi = warp_first_true(le.rstart, le.c_len, [&](int s) { return (srow[s] - q0) >= gate; });
     int lo2 = le.lend, hi2 = le.lend;
-    if (le.lend > 0) lo2 = warp_first_true(0, le.lend, [&](int s) { return !((q0 - srow[s]) >= gate); });
+    if (a.cell_lo != nullptr) {
+      // two-level layout: coordinate 0 is ordered across chunks only -> whole chunks, bounds from the cell ranges
+      constexpr int TCL = chunk_len(D);
+      const int nch = (le.c_len + TCL - 1) / TCL;
+      if (le.rstart < le.c_len) {
+        const int c = warp_first_true(le.rstart / TCL, nch, [&](int j) { return (a.cell_lo[j] - q0) >= gate; });
+        hi = min(c * TCL, le.c_len);
+      }
+      if (le.lend > 0) {
+        const int c = warp_first_true(0, (le.lend + TCL - 1) / TCL, [&](int j) { return !((q0 - a.cell_hi[j]) >= gate); });
+        lo2 = min(c * TCL, le.lend);
+      }
+    } else {
+      if (le.rstart < le.c_len) hi = warp_first_true(le.rstart, le.c_len, [&](int s) { return (srow[s] - q0) >= gate; });
+      if (le.lend > 0) lo2 = warp_first_true(0, le.lend, [&](int s) { return !((q0 - srow[s]) >= gate); });
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const int b = pass == 0 ? lo : lo2, en = pass == 0 ? hi : hi2;
@@ -566,25 +766,6 @@ struct CountArgs {
   int* cnt_e1;           // out (E > 1)
   unsigned long long* pairs;
 };
-
-// first slot in [0, len) of the ascending array `a` whose value is >= v (NaN padding excluded by len)
-__device__ __forceinline__ int lower_bound_ge(const double* a, int len, double v) {
-  int lo = 0, hi = len;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-// first slot whose value is > v
-__device__ __forceinline__ int upper_bound_gt(const double* a, int len, double v) {
-  int lo = 0, hi = len;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] <= v) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 template <int C, int E, int QPT>
 __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count_kernel(const CountArgs a) {

@@ -11,6 +11,9 @@ cudaError_t launch_knn(int D, int qpt, const KnnArgs& args, int grid, cudaStream
 int knn_grid(int k, int ntiles, int sm_count);
 // finishes the queries knn_kernel deferred (register top-k variants only)
 cudaError_t launch_knn_leftover(int D, const KnnArgs& args, int grid, cudaStream_t stream);
+// two-level layout: per chunk of chunk_len(D) slots record the range of row1 and reorder by row2
+cudaError_t launch_cell_sort(int D, double* P, int64_t stride, int d, int* slot_row, int64_t n, int row1, int row2,
+                             double* cell_lo, double* cell_hi, int nchunks, cudaStream_t stream);
 // C shared + E private coordinates
 cudaError_t launch_count(int C, int E, int qpt, const CountArgs& args, int grid, cudaStream_t stream);
 }  // namespace eb2

@@ -163,6 +163,12 @@ struct PointSet {
   int* slot_row = nullptr;
   int sort_row = -1;
   std::vector<int> seg_slot, seg_len;   // per segment
+  // two-level layout (see cell_sort_kernel): chunks of chunk_len(cell_dim) slots ordered by cell_row2 inside
+  int cell_dim = 0;
+  int cell_row2 = -1;
+  double* cell_lo = nullptr;
+  double* cell_hi = nullptr;
+  const double* sorted_keys = nullptr;   // sort_row values in ascending order (n of them), when sorted
 };
 
 template <typename K, typename V>
@@ -181,8 +187,10 @@ void sort_keys(Scratch& s, const double* kin, double* kout, int n) {
 }
 
 // raw: d x n on the device.  cls: class id per row on the device (or NULL), class_size: rows per class.
+// cell_dim > 0 asks for the two-level layout for a search space of that dimension whose coordinate 1 is
+// row cell_row2 (single-segment sets only)
 PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const int* cls,
-                         const std::vector<int>& class_size, int sort_row) {
+                         const std::vector<int>& class_size, int sort_row, int cell_dim = 0, int cell_row2 = -1) {
   cudaStream_t st = s.c.stream;
   PointSet ps;
   ps.d = d;
@@ -218,6 +226,7 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
     int* p1 = s.dev<int>(n);
     sort_pairs<double, int>(s, raw + static_cast<int64_t>(sort_row) * n, keys_out, iota, p1, static_cast<int>(n), 0, 64);
     perm = p1;
+    ps.sorted_keys = keys_out;
     if (cls) {
       // stable second pass by class keeps the coordinate order inside each class
       int* cls_by_rank = s.dev<int>(n);
@@ -264,6 +273,16 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   gather_kernel<<<blocks_n, 256, 0, st>>>(ga);
   s.launches++;
   CU(cudaGetLastError());
+  if (cell_dim >= 2 && cell_row2 >= 0 && sort_row >= 0 && !cls && !getenv("EB2_NO_CELLS")) {
+    const int tc = chunk_len(cell_dim);
+    const int nchunks = cdiv(n, tc);
+    ps.cell_dim = cell_dim;
+    ps.cell_row2 = cell_row2;
+    ps.cell_lo = s.dev<double>(nchunks);
+    ps.cell_hi = s.dev<double>(nchunks);
+    CU(launch_cell_sort(cell_dim, ps.P, ps.stride, d, ps.slot_row, n, sort_row, cell_row2, ps.cell_lo, ps.cell_hi, nchunks, st));
+    s.launches++;
+  }
   return ps;
 }
 
@@ -329,14 +348,23 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
   KnnArgs a;
   a.P = ps.P; a.stride = ps.stride; a.rows = rows; a.tiles = ts.dev; a.k = k;
   a.sort_row = -1;
+  a.cell_lo = nullptr; a.cell_hi = nullptr;
   // pruning needs the sorted coordinate to be a coordinate of the search space; the kernel reads it
   // as the query's coordinate 0 (the order of coordinates is irrelevant to the max-norm)
   for (int t = 0; t < D && ps.sort_row >= 0; ++t)
-    if (rows.row[t] == ps.sort_row) { std::swap(a.rows.row[0], a.rows.row[t]); a.sort_row = ps.sort_row; break; } a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
+    if (rows.row[t] == ps.sort_row) { std::swap(a.rows.row[0], a.rows.row[t]); a.sort_row = ps.sort_row; break; }
+  if (a.sort_row >= 0 && ps.cell_lo && ps.cell_dim == D) {
+    // two-level layout: the in-chunk coordinate must be coordinate 1 of the search space
+    for (int t = 1; t < D; ++t)
+      if (a.rows.row[t] == ps.cell_row2) { std::swap(a.rows.row[1], a.rows.row[t]); a.cell_lo = ps.cell_lo; a.cell_hi = ps.cell_hi; break; }
+    if (!a.cell_lo) throw CudaFail{cudaErrorInvalidValue, "cell layout does not match the search space", __LINE__};
+  } else if (ps.cell_lo) {
+    throw CudaFail{cudaErrorInvalidValue, "cell layout used with a different search space", __LINE__};
+  } a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
   a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
   const int k1t = (k + 1 <= 4) ? 4 : 8;
   if (a.sort_row >= 0 && k + 1 <= 8) {
-    a.defer_below = 16;
+    a.defer_below = a.cell_lo ? 4 : 16;      // measured optima (tools/exp_defer.py)
     if (const char* e = getenv("EB2_DEFER")) a.defer_below = atoi(e);     // tuning knob
   }
   if (a.defer_below > 0) {
@@ -739,7 +767,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     CallInit ci = begin_call(s);
     const double* raw = stage_input(s, in, 2, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
-    PointSet ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1);
+    PointSet ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
     double* eps = s.dev<double>(ps.stride);
@@ -754,7 +782,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
       CountOut out; out.e0 = nx; out.e1 = ny;
       run_count(s, ps, ps, 0, 2, RowSel{}, RowSel{}, rows_range(0, 2), rows_range(0, 2), radius, self, false, out, ci.pairs);
     } else {
-      const double* xs = ps.P;                       // row 0 is already ascending when the set is sorted by x
+      const double* xs = ps.sorted_keys;             // x in ascending order, by-product of the layout sort
       if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
       double* ys = s.dev<double>(n);
       sort_keys(s, raw + n, ys, (int)n);
@@ -1004,7 +1032,7 @@ int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uin
     CallInit ci = begin_call(s);
     const double* raw = stage_coords(s, coords, m, n, flags, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
-    PointSet ps = build_point_set(s, raw, m, n, nullptr, {}, prune ? 0 : -1);
+    PointSet ps = build_point_set(s, raw, m, n, nullptr, {}, prune ? 0 : -1, m, m >= 2 ? 1 : -1);
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
     double* dist = s.dev<double>(ps.stride);
