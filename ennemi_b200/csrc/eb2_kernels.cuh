@@ -688,44 +688,69 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
     const double* srow = a.P + a.sort_row * a.stride + le.c_lo;
     const double q0 = q[0];
     // candidates that can still enter: gap in the sorted coordinate below the gate (monotone => exact)
-    int lo = le.rstart, hi = le.rstart;
-    int lo2 = le.lend, hi2 = le.lend;
     if (a.cell_lo != nullptr) {
-      // two-level layout: coordinate 0 is ordered across chunks only -> whole chunks, bounds from the cell ranges
-      constexpr int TCL = chunk_len(D);
-      const int nch = (le.c_len + TCL - 1) / TCL;
-      if (le.rstart < le.c_len) {
-        const int c = warp_first_true(le.rstart / TCL, nch, [&](int j) { return (a.cell_lo[j] - q0) >= gate; });
-        hi = min(c * TCL, le.c_len);
-      }
-      if (le.lend > 0) {
-        const int c = warp_first_true(0, (le.lend + TCL - 1) / TCL, [&](int j) { return !((q0 - a.cell_hi[j]) >= gate); });
-        lo2 = min(c * TCL, le.lend);
-      }
-    } else {
-      if (le.rstart < le.c_len) hi = warp_first_true(le.rstart, le.c_len, [&](int s) { return (srow[s] - q0) >= gate; });
-      if (le.lend > 0) lo2 = warp_first_true(0, le.lend, [&](int s) { return !((q0 - srow[s]) >= gate); });
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int b = pass == 0 ? lo : lo2, en = pass == 0 ? hi : hi2;
-      for (int base = b; base < en; base += kThreads * U) {
-        double c[U][D];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = min(base + u * kThreads + tid, en - 1);
-#pragma unroll
-          for (int t = 0; t < D; ++t) c[u][t] = a.P[a.rows.row[t] * a.stride + le.c_lo + j];
+      if constexpr (D >= 2) {
+        // two-level layout: coordinate 0 is ordered across chunks, coordinate 1 inside each chunk.  Chunks whose
+        // range of coordinate 0 can still matter are dealt to the warps; inside a chunk a warp-cooperative
+        // search on the (ascending) coordinate-1 row gives the slots that can matter; the lanes scan those.
+        constexpr int TCL = chunk_len(D);
+        const int nch = (le.c_len + TCL - 1) / TCL;
+        int r_lo = nch, r_hi = nch, l_lo = 0, l_hi = 0;
+        if (le.rstart < le.c_len) {
+          r_lo = le.rstart / TCL;
+          r_hi = warp_first_true(r_lo, nch, [&](int j) { return (a.cell_lo[j] - q0) >= gate; });
         }
+        if (le.lend > 0) {
+          l_hi = (le.lend + TCL - 1) / TCL;
+          l_lo = warp_first_true(0, l_hi, [&](int j) { return !((q0 - a.cell_hi[j]) >= gate); });
+        }
+        const double slack = 8.881784197001252e-16;  // 2^-50
+        const double lo_v = (q[1] - gate) - (fabs(q[1]) + gate) * slack;
+        const double hi_v = (q[1] + gate) + (fabs(q[1]) + gate) * slack;
+        const int nr = r_hi - r_lo, nl = l_hi - l_lo;
+        for (int idx = warp; idx < nr + nl; idx += NW) {
+          const int c = idx < nr ? r_lo + idx : l_lo + (idx - nr);
+          const int base = c * TCL;
+          const int lenv = min(TCL, le.c_len - base);
+          const double* yrow = a.P + a.rows.row[1] * a.stride + le.c_lo + base;
+          const int wlo = warp_first_true(0, lenv, [&](int sidx_) { return yrow[sidx_] >= lo_v; });
+          const int whi = warp_first_true(wlo, lenv, [&](int sidx_) { return yrow[sidx_] > hi_v; });
+          for (int j = wlo + lane; j < whi; j += 32) {
+            double c_[D];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (base + u * kThreads + tid < en) {
-            const double m = cheb<D>(q, c[u]);
+            for (int t = 0; t < D; ++t) c_[t] = a.P[a.rows.row[t] * a.stride + le.c_lo + base + j];
+            const double m = cheb<D>(q, c_);
             if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
           }
+          if (lane == 0) npairs += (unsigned long long)(whi - wlo);
         }
       }
-      if (tid == 0) npairs += (unsigned long long)(en - b);
+    } else {
+      int lo = le.rstart, hi = le.rstart;
+      int lo2 = le.lend, hi2 = le.lend;
+      if (le.rstart < le.c_len) hi = warp_first_true(le.rstart, le.c_len, [&](int s) { return (srow[s] - q0) >= gate; });
+      if (le.lend > 0) lo2 = warp_first_true(0, le.lend, [&](int s) { return !((q0 - srow[s]) >= gate); });
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int b = pass == 0 ? lo : lo2, en = pass == 0 ? hi : hi2;
+        for (int base = b; base < en; base += kThreads * U) {
+          double c[U][D];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = min(base + u * kThreads + tid, en - 1);
+#pragma unroll
+            for (int t = 0; t < D; ++t) c[u][t] = a.P[a.rows.row[t] * a.stride + le.c_lo + j];
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (base + u * kThreads + tid < en) {
+              const double m = cheb<D>(q, c[u]);
+              if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
+            }
+          }
+        }
+        if (tid == 0) npairs += (unsigned long long)(en - b);
+      }
     }
     // per-warp merge -> shared; then warp 0 merges the NW warp lists and the stored list
     const double mine = warp_merge_lists<K1T>(best, K1T);
@@ -741,7 +766,7 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
     }
     __syncthreads();
   }
-  if (a.pairs && tid == 0 && npairs) atomicAdd(a.pairs, npairs);
+  if (a.pairs && (tid & 31) == 0 && npairs) atomicAdd(a.pairs, npairs);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -364,7 +364,7 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
   a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
   const int k1t = (k + 1 <= 4) ? 4 : 8;
   if (a.sort_row >= 0 && k + 1 <= 8) {
-    a.defer_below = a.cell_lo ? 4 : 16;      // measured optima (tools/exp_defer.py)
+    a.defer_below = a.cell_lo ? 8 : 16;      // measured optima (tools/exp_defer.py)
     if (const char* e = getenv("EB2_DEFER")) a.defer_below = atoi(e);     // tuning knob
   }
   if (a.defer_below > 0) {
