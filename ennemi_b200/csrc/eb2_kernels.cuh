@@ -786,6 +786,10 @@ struct CountArgs {
   int ntiles;
   int prune_q_row;       // row of Q / row of B holding the coordinate B is sorted by inside the segment, or -1
   int prune_b_row;
+  // two-level candidate layout (single segment, C >= 2): shared coordinate 0 ordered across chunks of
+  // chunk_len(C+E) slots, shared coordinate 1 inside each chunk; cell_lo/hi = range of coordinate 0 per chunk
+  const double* cell_lo;
+  const double* cell_hi;
   int* cnt_s;            // out per query slot (C > 0)
   int* cnt_e0;           // out (E > 0)
   int* cnt_e1;           // out (E > 1)
@@ -828,9 +832,10 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
     int ns[QPT], ne0[QPT], ne1[QPT];
     int qslot[QPT];
     bool valid[QPT];
+    const bool cells = C >= 2 && a.cell_lo != nullptr;
 #pragma unroll
     for (int i = 0; i < QPT; ++i) {
-      const int qi = tid + i * kThreads;
+      const int qi = cells ? QPT * tid + i : tid + i * kThreads;   // cells: a warp owns consecutive slots
       qslot[i] = qi;
       valid[i] = qi < tile.q_n;
       const int slot = tile.q_lo + qi;
@@ -845,7 +850,56 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
     const int len_pad = (tile.c_len + kSegAlign - 1) / kSegAlign * kSegAlign;
     int ch_lo = 0, ch_hi = (len_pad + TC - 1) / TC;   // chunk range [ch_lo, ch_hi) of the CTA
     int w_lo = ch_lo, w_hi = ch_hi;                   // ... and of this warp
-    if (a.prune_b_row >= 0) {
+    double y2lo = -kInf, y2hi = kInf;                 // cells: this warp's window in shared coordinate 1
+    if (cells) {
+      if constexpr (C >= 2) {
+        double vmin = kInf, vmax = -kInf, umin = kInf, umax = -kInf, rmax = -kInf;
+#pragma unroll
+        for (int i = 0; i < QPT; ++i) {
+          if (valid[i]) {
+            vmin = fmin(vmin, qs[i][0]); vmax = fmax(vmax, qs[i][0]);
+            umin = fmin(umin, qs[i][1]); umax = fmax(umax, qs[i][1]);
+            rmax = fmax(rmax, r[i]);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+          vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+          umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+          umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+          rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        }
+        const double slack = 8.881784197001252e-16;  // 2^-50
+        int c_lo = 0, c_hi = 0;
+        if (rmax >= 0.0) {   // otherwise nothing can be counted for this warp
+          const int nch = ch_hi;
+          const double lo_v = (vmin - rmax) - (fabs(vmin) + fabs(rmax)) * slack;
+          const double hi_v = (vmax + rmax) + (fabs(vmax) + fabs(rmax)) * slack;
+          if ((tid & 31) == 0) {
+            c_lo = lower_bound_ge(a.cell_hi, nch, lo_v);    // first chunk whose coordinate-0 range reaches lo_v
+            c_hi = upper_bound_gt(a.cell_lo, nch, hi_v);    // first chunk that starts beyond hi_v
+          }
+          c_lo = __shfl_sync(0xffffffffu, c_lo, 0);
+          c_hi = __shfl_sync(0xffffffffu, c_hi, 0);
+          y2lo = (umin - rmax) - (fabs(umin) + fabs(rmax)) * slack;
+          y2hi = (umax + rmax) + (fabs(umax) + fabs(rmax)) * slack;
+        }
+        w_lo = c_lo; w_hi = max(c_lo, c_hi);
+        if ((tid & 31) == 0) {
+          wrange[2 * (tid >> 5)] = w_hi > w_lo ? w_lo : 0x7fffffff;
+          wrange[2 * (tid >> 5) + 1] = w_hi > w_lo ? w_hi : 0;
+        }
+        __syncthreads();
+        ch_lo = 0x7fffffff; ch_hi = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+          ch_lo = min(ch_lo, wrange[2 * w]);
+          ch_hi = max(ch_hi, wrange[2 * w + 1]);
+        }
+        __syncthreads();
+      }
+    } else if (a.prune_b_row >= 0) {
       // the pruning coordinate is the first shared one (or the only extra one): host guarantees it
       // 1. regroup the tile's queries by radius so that warps are homogeneous
 #pragma unroll
@@ -929,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
       __syncthreads();
     }
     unsigned long long npairs = 0;
-    const bool dense_hits = a.prune_b_row >= 0;
+    const bool dense_hits = a.prune_b_row >= 0 || cells;
 
     for (int j = ch_lo; j < ch_hi; ++j) {
       const int c_off = j * TC;
@@ -938,9 +992,18 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
       mbar_wait(&bar, phase);
       phase ^= 1;
       if (j >= w_lo && j < w_hi) {
-        if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - c_off) * 32 * QPT;
+        int jlo = 0, jhi = len;
+        if (cells) {     // slots of this chunk whose shared coordinate 1 (ascending inside the chunk) can matter
+          const int lenv = min(TC, tile.c_len - c_off);
+          const double* sy = sbuf + TC;
+          jlo = lower_bound_ge(sy, lenv, y2lo) & ~(kGroup - 1);
+          jhi = min(len, (upper_bound_gt(sy, lenv, y2hi) + kGroup - 1) & ~(kGroup - 1));
+          if ((tid & 31) == 0) npairs += (unsigned long long)max(0, jhi - jlo) * 32 * QPT;
+        } else {
+          if ((tid & 31) == 0) npairs += (unsigned long long)min(TC, tile.c_len - c_off) * 32 * QPT;
+        }
 #pragma unroll 1
-        for (int jj = 0; jj < len; jj += kGroup) {
+        for (int jj = jlo; jj < jhi; jj += kGroup) {
           double c[kGroup][D];
 #pragma unroll
           for (int t = 0; t < D; ++t) {

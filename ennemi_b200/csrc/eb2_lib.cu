@@ -412,6 +412,25 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
       }
     if (C == 0 && E == 1 && b_erow.row[0] == bs.sort_row) { a.prune_b_row = bs.sort_row; a.prune_q_row = q_erow.row[0]; }
   }
+  a.cell_lo = nullptr; a.cell_hi = nullptr;
+  if (bs.cell_lo) {
+    // two-level candidate layout: usable when queries come from the same set, the chunk length matches and
+    // the ordering coordinates are shared coordinates 0 and 1 of the marginals; otherwise no pruning at all
+    a.prune_q_row = -1; a.prune_b_row = -1;
+    if (prune && &qs == &bs && C >= 2 && bs.cell_dim > 0 && chunk_len(bs.cell_dim) == chunk_len(C + E)) {
+      int i0 = -1, i1 = -1;
+      for (int t = 0; t < C; ++t) {
+        if (a.b_srow.row[t] == bs.sort_row) i0 = t;
+        if (a.b_srow.row[t] == bs.cell_row2) i1 = t;
+      }
+      if (i0 >= 0 && i1 >= 0) {
+        std::swap(a.b_srow.row[0], a.b_srow.row[i0]); std::swap(a.q_srow.row[0], a.q_srow.row[i0]);
+        if (i1 == 0) i1 = i0;
+        std::swap(a.b_srow.row[1], a.b_srow.row[i1]); std::swap(a.q_srow.row[1], a.q_srow.row[i1]);
+        a.cell_lo = bs.cell_lo; a.cell_hi = bs.cell_hi;
+      }
+    }
+  }
   a.cnt_s = out.s; a.cnt_e0 = out.e0; a.cnt_e1 = out.e1; a.pairs = pairs;
   CU(launch_count(C, E, qs.qpt, a, ts.count, s.c.stream));
   s.launches++;
@@ -852,7 +871,8 @@ static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, 
     const double* raw = stage_input(s, in, d, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
     // every space on this path (xyz, xz, yz, z) contains z_0: sort by it
-    PointSet ps = build_point_set(s, raw, d, n, nullptr, {}, prune ? 2 : -1);
+    // ... and, with a condition of 2+ dimensions, order the slots inside each chunk by z_1 (two-level layout)
+    PointSet ps = build_point_set(s, raw, d, n, nullptr, {}, prune ? 2 : -1, c_dim >= 2 ? d : 0, c_dim >= 2 ? 3 : -1);
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
     double* eps = s.dev<double>(ps.stride);
