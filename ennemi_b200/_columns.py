@@ -182,7 +182,7 @@ class ColsTask:
             self.store.ensure(dev, key)
             mean, std, nkey = 0.0, 0.0, 0
             if self.preprocess:
-                mean, std = self.store.stats(tag, lambda: window_stats(view))
+                mean, std = self.store.stats(tag, stats_of(key, off, view))
                 if abs(std) < _align.CONSTANT_STD:
                     warnings.warn(_align.CONSTANT_DATA_WARNING)
                     std = 0.0
@@ -194,16 +194,22 @@ class ColsTask:
                     std = 0.0
             return _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
 
+        device_stats = n >= DEVICE_STATS_MIN_ROWS
+
+        def stats_of(key, off, view):
+            if device_stats:      # NumPy-exact pairwise mean/std where the column already is (eb2_cache_stats)
+                return lambda: _native.cache_stats(key, off, n, dev=dev)
+            return lambda: window_stats(view)
+
         if n >= OVERLAP_MIN_ROWS and self.preprocess and self.store.missing(dev, self.xkey, self.ykey):
-            # large first-time windows: x's upload overlaps y's statistics and vice versa (both release the GIL)
-            def side(key, off, view, upload_first):
-                if upload_first:
-                    self.store.ensure(dev, key)
-                self.store.stats((key, off, n), lambda: window_stats(view))
-                if not upload_first:
-                    self.store.ensure(dev, key)
-            fut = _helper_pool().submit(side, self.ykey, y_off, ys, False)     # y: statistics, then upload
-            side(self.xkey, x_off, xs, True)                                   # x: upload, then statistics
+            # large first-time windows: the two uploads (and statistics) run side by side on two stream lanes
+            def side(key, off, view, lane_dev):
+                self.store.ensure(lane_dev, key)
+                self.store.stats((key, off, n), (lambda: _native.cache_stats(key, off, n, dev=lane_dev)) if device_stats
+                                 else (lambda: window_stats(view)))
+            other = _devices.with_lane(dev, ((dev >> 8) + 1) % 4)
+            fut = _helper_pool().submit(side, self.ykey, y_off, ys, other)
+            side(self.xkey, x_off, xs, dev)
             fut.result()
         descs.append(one(self.xkey, x_off, xs, (self.xkey, x_off, n)))
         descs.append(one(self.ykey, y_off, ys, (self.ykey, y_off, n)))
@@ -256,6 +262,7 @@ class ColsTask:
 
 
 OVERLAP_MIN_ROWS = 200_000
+DEVICE_STATS_MIN_ROWS = 50_000     # above this the window statistics are computed on the device
 _pool = None
 _pool_lock = threading.Lock()
 

@@ -32,7 +32,7 @@ EXPORTS = (
     "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
-    "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows",
+    "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
 )
 
 _lib = None
@@ -92,6 +92,7 @@ def load():
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
         lib.eb2_ksg_mi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _i64, _i64, _c_dp]
         lib.eb2_cmi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _i64, _i64, _c_dp]
+        lib.eb2_cache_stats.argtypes = [_int, ctypes.c_uint64, _i64, _i64, _i64, _c_dp, _c_dp]
         lib.eb2_mi_cols_batch.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _i64, _int, _u32, _c_dp, ctypes.POINTER(_int)]
         for name in EXPORTS:
             getattr(lib, name)
@@ -394,3 +395,14 @@ def mi_cols_rows(cols, n: int, k: int, row_lo: int, row_hi: int, dev: int = 0, f
     if rc:
         _raise(rc)
     return partial
+
+
+def cache_stats(key: int, off: int, n: int, stride: int = 1, dev: int = 0):
+    """(mean, std) of a cached column window with NumPy's summation order (bit-identical to
+    ``view.mean()``, ``view.std()``), computed on the device."""
+    lib = load()
+    mean, std = ctypes.c_double(), ctypes.c_double()
+    rc = lib.eb2_cache_stats(dev, key, off, stride, n, ctypes.byref(mean), ctypes.byref(std))
+    if rc:
+        _raise(rc)
+    return mean.value, std.value

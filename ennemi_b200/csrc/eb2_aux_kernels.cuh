@@ -225,6 +225,92 @@ __global__ void prep_kernel(const PrepArgs a) {
   a.raw[idx] = v;
 }
 
+// ---- NumPy-exact mean / standard deviation of a cached column window ------------------------------
+// np.add.reduce on float64 is a fixed pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+// DOUBLE_pairwise_sum): blocks of <= 128 elements are summed with 8 interleaved accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail; larger ranges split at n/2 rounded down to a
+// multiple of 8, recursively.  Reproducing that association exactly gives the same bits as ndarray.mean()
+// / ndarray.std() (tests/test_gpu_api.py checks it), so the statistics the rescaling uses can be computed
+// where the data already is.  The host supplies the leaf table of the recursion for this n.
+struct NpLeaf {
+  long long off;   // first element of the leaf (window-relative)
+  int len;         // <= 128
+};
+
+// one thread per leaf; mode 0: sum of x, mode 1: sum of (x - mean)^2 with mean read from *mean_ptr
+__global__ void np_leaf_sum_kernel(const double* src, long long off, long long stride, const NpLeaf* leaves, int nleaves,
+                                   int mode, const double* mean_ptr, double* leaf_sum) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nleaves) return;
+  const NpLeaf lf = leaves[t];
+  const double mean = mode ? *mean_ptr : 0.0;
+  const double* p = src + off + lf.off * stride;
+  auto at = [&](int i) {
+    const double v = p[(long long)i * stride];
+    if (mode == 0) return v;
+    const double c = __dsub_rn(v, mean);
+    return __dmul_rn(c, c);
+  };
+  const int n = lf.len;
+  double res;
+  if (n < 8) {
+    res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, at(i));
+  } else {
+    double r0 = at(0), r1 = at(1), r2 = at(2), r3 = at(3), r4 = at(4), r5 = at(5), r6 = at(6), r7 = at(7);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+      r0 = __dadd_rn(r0, at(i)); r1 = __dadd_rn(r1, at(i + 1)); r2 = __dadd_rn(r2, at(i + 2)); r3 = __dadd_rn(r3, at(i + 3));
+      r4 = __dadd_rn(r4, at(i + 4)); r5 = __dadd_rn(r5, at(i + 5)); r6 = __dadd_rn(r6, at(i + 6)); r7 = __dadd_rn(r7, at(i + 7));
+    }
+    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (; i < n; ++i) res = __dadd_rn(res, at(i));
+  }
+  leaf_sum[t] = res;
+}
+
+// the recursion above the leaves; `next` walks the leaf sums in order
+__device__ double np_combine(const double* leaf_sum, int& next, long long n) {
+  if (n <= 128) return leaf_sum[next++];
+  long long n2 = n / 2;
+  n2 -= n2 % 8;
+  const double a = np_combine(leaf_sum, next, n2);
+  const double b = np_combine(leaf_sum, next, n - n2);
+  return __dadd_rn(a, b);
+}
+
+// sub-trees (first leaf, element count) are summed by one thread each, then thread 0 walks the top of the tree
+struct NpSub {
+  int first_leaf;
+  long long n;
+};
+__device__ double np_combine_top(const double* sub_sum, int& next, long long n, int depth, int top_depth) {
+  if (depth == top_depth || n <= 128) return sub_sum[next++];
+  long long n2 = n / 2;
+  n2 -= n2 % 8;
+  const double a = np_combine_top(sub_sum, next, n2, depth + 1, top_depth);
+  const double b = np_combine_top(sub_sum, next, n - n2, depth + 1, top_depth);
+  return __dadd_rn(a, b);
+}
+// out[0] = total; finish: 0 -> out[1] = total / n (the mean); 1 -> out[1] = sqrt(total / n) (the std)
+__global__ void np_combine_kernel(const double* leaf_sum, const NpSub* subs, int nsubs, long long n, int top_depth,
+                                  int finish, double* out) {
+  __shared__ double sub_sum[256];
+  const int t = threadIdx.x;
+  if (t < nsubs) {
+    int next = subs[t].first_leaf;
+    sub_sum[t] = np_combine(leaf_sum, next, subs[t].n);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int next = 0;
+    const double total = np_combine_top(sub_sum, next, n, 0, top_depth);
+    out[0] = total;
+    const double q = __ddiv_rn(total, (double)n);
+    out[1] = finish ? __dsqrt_rn(q) : q;
+  }
+}
+
 // register-resident DADD chains: the FP64 issue rate that bounds the all-pairs kernels
 __global__ void fp64_peak_kernel(double* out, double c, int iters) {
   double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

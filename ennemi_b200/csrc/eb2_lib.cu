@@ -760,6 +760,67 @@ int eb2_cache_drop(int dev, uint64_t key) {
 
 int eb2_last_data_flags(void) { return g_data_flags; }
 
+// leaf / sub-tree tables of NumPy's pairwise summation for a range of n elements
+static void np_plan(long long n, long long off, int depth, int top_depth, std::vector<NpLeaf>& leaves, std::vector<NpSub>& subs) {
+  // a sub-tree root is a node at top_depth, or a leaf that sits above it
+  if (depth == top_depth || (depth < top_depth && n <= 128)) subs.push_back(NpSub{static_cast<int>(leaves.size()), n});
+  if (n <= 128) {
+    leaves.push_back(NpLeaf{off, static_cast<int>(n)});
+    return;
+  }
+  long long n2 = n / 2;
+  n2 -= n2 % 8;
+  np_plan(n2, off, depth + 1, top_depth, leaves, subs);
+  np_plan(n - n2, off + n2, depth + 1, top_depth, leaves, subs);
+}
+
+int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t n, double* mean, double* std_out) {
+  if (key == 0 || n <= 0 || stride == 0 || !mean || !std_out) return fail(EB2_ERR_ARG, "eb2_cache_stats: bad argument");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    const double* src = nullptr;
+    {
+      std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+      auto it = c.shared->cache.find(key);
+      if (it == c.shared->cache.end()) return fail(EB2_ERR_ARG, "eb2_cache_stats: column key not in the device cache");
+      const int64_t last = off + (n - 1) * stride;
+      if (off < 0 || last < 0 || off >= it->second.second || last >= it->second.second)
+        return fail(EB2_ERR_ARG, "eb2_cache_stats: window outside the cached column");
+      src = it->second.first;
+    }
+    const int top_depth = 7;                       // <= 128 sub-trees
+    std::vector<NpLeaf> leaves;
+    std::vector<NpSub> subs;
+    leaves.reserve(static_cast<size_t>(n / 64 + 2));
+    np_plan(n, 0, 0, top_depth, leaves, subs);
+    const int nleaves = static_cast<int>(leaves.size()), nsubs = static_cast<int>(subs.size());
+    NpLeaf* hl = s.host<NpLeaf>(leaves.size());
+    NpSub* hs = s.host<NpSub>(subs.size());
+    std::memcpy(hl, leaves.data(), sizeof(NpLeaf) * leaves.size());
+    std::memcpy(hs, subs.data(), sizeof(NpSub) * subs.size());
+    NpLeaf* dl = s.dev<NpLeaf>(leaves.size());
+    NpSub* ds = s.dev<NpSub>(subs.size());
+    double* leaf_sum = s.dev<double>(leaves.size());
+    double* out = s.dev<double>(4);
+    CU(cudaMemcpyAsync(dl, hl, sizeof(NpLeaf) * leaves.size(), cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(ds, hs, sizeof(NpSub) * subs.size(), cudaMemcpyHostToDevice, c.stream));
+    const int blocks = cdiv(nleaves, 128);
+    np_leaf_sum_kernel<<<blocks, 128, 0, c.stream>>>(src, off, stride, dl, nleaves, 0, nullptr, leaf_sum);
+    np_combine_kernel<<<1, 256, 0, c.stream>>>(leaf_sum, ds, nsubs, n, top_depth, 0, out);          // out[1] = mean
+    np_leaf_sum_kernel<<<blocks, 128, 0, c.stream>>>(src, off, stride, dl, nleaves, 1, out + 1, leaf_sum);
+    np_combine_kernel<<<1, 256, 0, c.stream>>>(leaf_sum, ds, nsubs, n, top_depth, 1, out + 2);      // out[3] = std
+    CU(cudaGetLastError());
+    double* h = s.host<double>(4);
+    CU(cudaMemcpyAsync(h, out, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    *mean = h[1];
+    *std_out = h[3];
+    c.last_launches = 4;
+    return EB2_OK;
+  });
+}
+
 // Many tasks of one shape in one call: no interpreter work and no GIL between tasks.  Task t uses
 // cols[t * d .. t * d + d).  status[t] = 0, or EB2_ERR_* | data_flags << 8 with values[t] = NaN; the
 // call itself fails only on bad arguments.

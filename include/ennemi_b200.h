@@ -138,6 +138,11 @@ EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
 EB2_API int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n);  /* key != 0; replaces */
 EB2_API int eb2_cache_drop(int dev, uint64_t key);                               /* key == 0: everything */
 
+/* mean and standard deviation (ddof = 0) of the window column[key][off + i*stride], i in [0, n), computed on the
+ * device with NumPy's pairwise-summation association, i.e. the same bits as ndarray.mean() / ndarray.std()
+ * (the values _rescale_data uses, ennemi/_driver.py:878-882). */
+EB2_API int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t n, double* mean, double* std);
+
 /* coordinate t of the joint space, for i in [0, n):
  *   v_i = column[key][off + i * stride]
  *   if (std != 0)  v_i = (v_i - mean) / std  and, if nkey != 0,  v_i += column[nkey][noff + i * nstride] */

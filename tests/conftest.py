@@ -40,7 +40,7 @@ class OracleBackend:
     signatures, answers computed by the CPU oracle.  Never used by the product."""
 
     PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
-               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch")
+               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch", "cache_stats")
 
     def __init__(self, backend="scipy"):
         import oracle
@@ -81,23 +81,27 @@ class OracleBackend:
 
     # ---- device column cache, emulated with numpy (same three IEEE operations as prep_kernel)
     def cache_put(self, key, column, dev=0):
-        self.cache[(dev, key)] = np.array(column, dtype=np.float64).ravel()
+        self.cache[(dev & 0xFF, key)] = np.array(column, dtype=np.float64).ravel()
 
     def cache_drop(self, key, dev=0):
-        self.cache.pop((dev, key), None)
+        self.cache.pop((dev & 0xFF, key), None)
+
+    def cache_stats(self, key, off, n, stride=1, dev=0):
+        v = self.cache[(dev & 0xFF, key)][off: off + (n - 1) * stride + 1: stride]
+        return float(v.mean()), float(v.std())
 
     def _gather(self, descs, n, dev):
         from ennemi_b200 import _native
         rows = []
         for d in descs:
-            col = self.cache[(dev, d.key)]
+            col = self.cache[(dev & 0xFF, d.key)]
             v = col[d.off: d.off + (n - 1) * d.stride + 1: d.stride].copy()
             if np.isnan(v).any():
                 raise _native.NonFiniteInput("data must be finite, check for nan or inf values", True)
             if d.std != 0.0:
                 v = (v - d.mean) / d.std
                 if d.nkey:
-                    noise = self.cache[(dev, d.nkey)]
+                    noise = self.cache[(dev & 0xFF, d.nkey)]
                     v = v + noise[d.noff: d.noff + (n - 1) * d.nstride + 1: d.nstride]
             if not np.isfinite(v).all():
                 raise _native.NonFiniteInput("data must be finite, check for nan or inf values", False)

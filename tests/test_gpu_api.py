@@ -130,3 +130,23 @@ def test_device_column_path_on_gpu(golden_api, monkeypatch):
         eb.estimate_mi(np.where(np.arange(600) == 5, np.nan, yy), x3)
     with pytest.raises(ValueError, match="data must be finite"):
         eb.estimate_mi(yy, np.where(np.arange(600) == 7, np.inf, x3[:, 0]), preprocess=False)
+
+
+def test_device_statistics_have_numpy_bits():
+    """eb2_cache_stats reproduces ndarray.mean() / ndarray.std() bit for bit (NumPy's pairwise summation order)
+    for window sizes around every branch of the recursion, offsets and strides."""
+    from ennemi_b200 import _native as nat
+    rng = np.random.default_rng(5)
+    col = rng.normal(3.0, 2.5, size=1_200_000)
+    nat.cache_put(777001, col)
+    try:
+        for n in (1, 5, 7, 8, 9, 127, 128, 129, 136, 255, 256, 257, 1000, 4097, 50_000, 99_991, 262_144, 1_000_000, 1_200_000):
+            for off in (0, 3):
+                if off + n > col.size:
+                    continue
+                view = col[off: off + n]
+                assert nat.cache_stats(777001, off, n) == (float(view.mean()), float(view.std())), (n, off)
+        view = col[5: 5 + 3 * 100_000: 3]
+        assert nat.cache_stats(777001, 5, 100_000, stride=3) == (float(view.mean()), float(view.std()))
+    finally:
+        nat.cache_drop(777001)
