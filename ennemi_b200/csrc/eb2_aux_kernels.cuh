@@ -137,7 +137,7 @@ __global__ void iota_kernel(int* v, int n) {
 // rank -> padded slot.  Unsegmented: slot = rank.  Segmented: ranks are class-major, class c owns
 // ranks [seg_rank[c], seg_rank[c+1]) and slots starting at seg_slot[c].
 struct GatherArgs {
-  const double* raw;      // d x n dimension-major input
+  const double* rows[kMaxDim + 1];   // source of each of the d rows (n values, caller's row order)
   int64_t n;
   int d;
   const int* perm;        // rank -> input row (NULL: identity)
@@ -158,7 +158,7 @@ __global__ void gather_kernel(const GatherArgs a) {
     const int c = a.cls_sorted[rank];
     slot = a.seg_slot[c] + (rank - a.seg_rank[c]);
   }
-  for (int t = 0; t < a.d; ++t) a.P[t * a.stride + slot] = a.raw[t * a.n + row];
+  for (int t = 0; t < a.d; ++t) a.P[t * a.stride + slot] = a.rows[t][row];
   a.slot_row[slot] = row;
 }
 
@@ -309,6 +309,11 @@ __global__ void np_combine_kernel(const double* leaf_sum, const NpSub* subs, int
     const double q = __ddiv_rn(total, (double)n);
     out[1] = finish ? __dsqrt_rn(q) : q;
   }
+}
+
+__global__ void or_flags_kernel(int* dst, const int* a, const int* b) {
+  const int v = (a ? *a : 0) | (b ? *b : 0);
+  if (v) atomicOr(dst, v);
 }
 
 // register-resident DADD chains: the FP64 issue rate that bounds the all-pairs kernels

@@ -63,9 +63,21 @@ constexpr int kNumEvents = 8;
 
 // device-resident columns (raw observations, noise vectors) uploaded once and referenced by key;
 // shared by the lanes of a device
+// a prepared variable (cached column window after rescaling + noise) and its ascending order; shared by
+// every task of a call that uses the same descriptor (pairwise_mi: each column 63 times per role)
+struct Derived {
+  double* vals = nullptr;     // n prepared values, caller's row order
+  double* sorted = nullptr;   // ascending
+  int* perm = nullptr;        // rank -> row
+  int* dflag = nullptr;       // bit0: NaN among the inputs, bit1: non-finite prepared value
+  cudaEvent_t ready = nullptr;
+  uint64_t src_key = 0, noise_key = 0;
+  int64_t n = 0;
+};
 struct DevShared {
   std::mutex mu;
   std::unordered_map<uint64_t, std::pair<double*, int64_t>> cache;
+  std::unordered_map<std::string, Derived> derived;
 };
 DevShared g_shared[kMaxDev];
 
@@ -104,6 +116,19 @@ Ctx& get_ctx(int dev_lane) {
   CU(cudaDeviceGetDefaultMemPool(&pool, dev));
   uint64_t keep = std::numeric_limits<uint64_t>::max();   // keep freed workspace cached in the pool
   CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (lane == 0) {
+    // reserve workspace once: the pool keeps it (release threshold above), so the first large call does not
+    // pay for growing the pool allocation by allocation
+    void* warm = nullptr;
+    size_t want = size_t(2) << 30;
+    if (const char* e = getenv("EB2_POOL_MB")) want = size_t(atoll(e)) << 20;
+    if (want && cudaMallocAsync(&warm, want, c.stream) == cudaSuccess) {
+      cudaFreeAsync(warm, c.stream);
+      cudaStreamSynchronize(c.stream);
+    } else {
+      cudaGetLastError();
+    }
+  }
   c.pinned_cap = 4 << 20;
   CU(cudaMallocHost(reinterpret_cast<void**>(&c.pinned), c.pinned_cap));
   c.dev = dev;
@@ -189,8 +214,24 @@ void sort_keys(Scratch& s, const double* kin, double* kout, int n) {
 // raw: d x n on the device.  cls: class id per row on the device (or NULL), class_size: rows per class.
 // cell_dim > 0 asks for the two-level layout for a search space of that dimension whose coordinate 1 is
 // row cell_row2 (single-segment sets only)
+struct Presorted {
+  const double* sorted_keys;   // row `sort_row` in ascending order
+  const int* perm;             // rank -> row
+};
+PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, int64_t n, const int* cls,
+                              const std::vector<int>& class_size, int sort_row, int cell_dim, int cell_row2,
+                              const Presorted* pre);
+
 PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const int* cls,
                          const std::vector<int>& class_size, int sort_row, int cell_dim = 0, int cell_row2 = -1) {
+  const double* rows[kMaxDim + 1];
+  for (int t = 0; t < d; ++t) rows[t] = raw + static_cast<int64_t>(t) * n;
+  return build_point_set_rows(s, rows, d, n, cls, class_size, sort_row, cell_dim, cell_row2, nullptr);
+}
+
+PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, int64_t n, const int* cls,
+                              const std::vector<int>& class_size, int sort_row, int cell_dim, int cell_row2,
+                              const Presorted* pre) {
   cudaStream_t st = s.c.stream;
   PointSet ps;
   ps.d = d;
@@ -219,14 +260,21 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   const int* perm = nullptr;
   const int* cls_sorted = nullptr;
   if (sort_row >= 0) {
-    int* iota = s.dev<int>(n);
-    iota_kernel<<<blocks_n, 256, 0, st>>>(iota, static_cast<int>(n));
-    s.launches++;
-    double* keys_out = s.dev<double>(n);
-    int* p1 = s.dev<int>(n);
-    sort_pairs<double, int>(s, raw + static_cast<int64_t>(sort_row) * n, keys_out, iota, p1, static_cast<int>(n), 0, 64);
+    const int* p1 = nullptr;
+    if (pre) {
+      p1 = pre->perm;
+      ps.sorted_keys = pre->sorted_keys;
+    } else {
+      int* iota = s.dev<int>(n);
+      iota_kernel<<<blocks_n, 256, 0, st>>>(iota, static_cast<int>(n));
+      s.launches++;
+      double* keys_out = s.dev<double>(n);
+      int* pp = s.dev<int>(n);
+      sort_pairs<double, int>(s, row_src[sort_row], keys_out, iota, pp, static_cast<int>(n), 0, 64);
+      p1 = pp;
+      ps.sorted_keys = keys_out;
+    }
     perm = p1;
-    ps.sorted_keys = keys_out;
     if (cls) {
       // stable second pass by class keeps the coordinate order inside each class
       int* cls_by_rank = s.dev<int>(n);
@@ -258,7 +306,8 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   CU(cudaMemsetAsync(ps.P, 0xFF, sizeof(double) * d * ps.stride, st));     // all-ones = NaN
   CU(cudaMemsetAsync(ps.slot_row, 0xFF, sizeof(int) * ps.stride, st));     // -1
   GatherArgs ga;
-  ga.raw = raw; ga.n = n; ga.d = d; ga.perm = perm; ga.cls_sorted = cls_sorted;
+  for (int t = 0; t < d; ++t) ga.rows[t] = row_src[t];
+  ga.n = n; ga.d = d; ga.perm = perm; ga.cls_sorted = cls_sorted;
   ga.seg_rank = nullptr; ga.seg_slot = nullptr;
   if (cls) {
     int* h = s.host<int>(2 * nseg);
@@ -519,6 +568,71 @@ const double* stage_coords(Scratch& s, const double* coords, int d, int64_t n, u
   return stage_input(s, in, d, n, nonfinite_flag);
 }
 
+// Prepared variable for a column descriptor, shared across the tasks (and stream lanes) of a call.
+// Created on first use on the caller's stream; other lanes wait on its event.
+Derived* get_derived(Scratch& s, const eb2_col_t& col, int64_t n) {
+  struct DKey { eb2_col_t c; int64_t n; } k;
+  std::memset(&k, 0, sizeof k);
+  k.c = col; k.n = n;
+  const std::string key(reinterpret_cast<const char*>(&k), sizeof k);
+  DevShared& sh = *s.c.shared;
+  std::lock_guard<std::mutex> guard(sh.mu);
+  auto it = sh.derived.find(key);
+  if (it == sh.derived.end()) {
+    auto src = sh.cache.find(col.key);
+    if (src == sh.cache.end()) throw CudaFail{cudaErrorInvalidValue, "column key not in the device cache", __LINE__};
+    const int64_t last = col.off + (n - 1) * col.stride;
+    if (col.off < 0 || last < 0 || col.off >= src->second.second || last >= src->second.second)
+      throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
+    PrepArgs pa;
+    pa.d = 1; pa.n = n;
+    PrepCol& pc = pa.col[0];
+    pc.src = src->second.first; pc.off = col.off; pc.stride = col.stride; pc.mean = col.mean; pc.std = col.std;
+    pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride;
+    if (col.nkey != 0) {
+      auto nt = sh.cache.find(col.nkey);
+      if (nt == sh.cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
+      const int64_t nlast = col.noff + (n - 1) * col.nstride;
+      if (col.noff < 0 || nlast < 0 || nlast >= nt->second.second)
+        throw CudaFail{cudaErrorInvalidValue, "noise slice outside the cached vector", __LINE__};
+      pc.noise = nt->second.first;
+    }
+    Derived d;
+    cudaStream_t st = s.c.stream;
+    d.n = n; d.src_key = col.key; d.noise_key = col.nkey;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.vals), sizeof(double) * n, st));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.sorted), sizeof(double) * n, st));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.perm), sizeof(int) * n, st));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.dflag), sizeof(int), st));
+    CU(cudaMemsetAsync(d.dflag, 0, sizeof(int), st));
+    pa.raw = d.vals; pa.flags = d.dflag;
+    prep_kernel<<<cdiv(n, 256), 256, 0, st>>>(pa);
+    nonfinite_kernel<<<cdiv(n, 256), 256, 0, st>>>(d.vals, n, d.dflag);
+    int* iota = s.dev<int>(n);
+    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, static_cast<int>(n));
+    s.launches += 3;
+    sort_pairs<double, int>(s, d.vals, d.sorted, iota, d.perm, static_cast<int>(n), 0, 64);
+    CU(cudaEventCreateWithFlags(&d.ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(d.ready, st));
+    it = sh.derived.emplace(key, d).first;
+  }
+  CU(cudaStreamWaitEvent(s.c.stream, it->second.ready, 0));
+  return &it->second;
+}
+
+void drop_derived_locked(DevShared& sh, uint64_t key, cudaStream_t st) {
+  for (auto it = sh.derived.begin(); it != sh.derived.end();) {
+    if (key == 0 || it->second.src_key == key || it->second.noise_key == key) {
+      cudaFreeAsync(it->second.vals, st); cudaFreeAsync(it->second.sorted, st);
+      cudaFreeAsync(it->second.perm, st); cudaFreeAsync(it->second.dflag, st);
+      cudaEventDestroy(it->second.ready);
+      it = sh.derived.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
 struct Outputs {
   double* eps = nullptr;     // host, caller's row order
   int64_t* cnt[3] = {nullptr, nullptr, nullptr};
@@ -698,6 +812,7 @@ int eb2_shutdown(void) {
     cudaStreamSynchronize(c.stream);
     {
       std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+      drop_derived_locked(*c.shared, 0, c.stream);
       for (auto& kv : c.shared->cache) cudaFreeAsync(kv.second.first, c.stream);
       c.shared->cache.clear();
     }
@@ -747,6 +862,7 @@ int eb2_cache_drop(int dev, uint64_t key) {
     CU(cudaSetDevice(c.dev));
     std::lock_guard<std::mutex> cache_guard(c.shared->mu);
     auto& cache = c.shared->cache;
+    drop_derived_locked(*c.shared, key, c.stream);
     if (key == 0) {
       for (auto& kv : cache) cudaFreeAsync(kv.second.first, c.stream);
       cache.clear();
@@ -845,9 +961,24 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CallInit ci = begin_call(s);
-    const double* raw = stage_input(s, in, 2, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
-    PointSet ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
+    const double* raw = nullptr;
+    const Derived* dx = nullptr;
+    const Derived* dy = nullptr;
+    PointSet ps;
+    if (in.cols && prune && !(flags & EB2_FLAG_BRUTE_COUNT) && !getenv("EB2_NO_DERIVED")) {
+      // prepared variables (rescaled values + their ascending order) are shared by all tasks of the call
+      dx = get_derived(s, in.cols[0], n);
+      dy = get_derived(s, in.cols[1], n);
+      or_flags_kernel<<<1, 1, 0, c.stream>>>(ci.nonfinite, dx->dflag, dy->dflag);
+      s.launches++;
+      const double* rows[2] = {dx->vals, dy->vals};
+      const Presorted pre{dx->sorted, dx->perm};
+      ps = build_point_set_rows(s, rows, 2, n, nullptr, {}, 0, 2, 1, &pre);
+    } else {
+      raw = stage_input(s, in, 2, n, ci.nonfinite);
+      ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
+    }
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
     double* eps = s.dev<double>(ps.stride);
@@ -864,8 +995,8 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     } else {
       const double* xs = ps.sorted_keys;             // x in ascending order, by-product of the layout sort
       if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
-      double* ys = s.dev<double>(n);
-      sort_keys(s, raw + n, ys, (int)n);
+      const double* ys = dy ? dy->sorted : nullptr;
+      if (!ys) { double* t = s.dev<double>(n); sort_keys(s, raw + n, t, (int)n); ys = t; }
       TileSet all = make_tiles(s, ps, row_lo, row_hi, false, 0, (int)n);
       run_search(s, ps.P, radius, xs, all, nx);
       run_search(s, ps.P + ps.stride, radius, ys, all, ny);
