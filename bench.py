@@ -227,7 +227,6 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_res, launches, knn_ms, pairs = timed_steps(step_resident, args.steps, args.warmup)
     ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
 
     # task fan-out (weak scaling): every rank estimates its own resident batch per step, no collective
     fan = None
@@ -271,6 +270,7 @@ def run_gpu(args):
         ms_b, _, knn_b, pairs_b = timed_steps(lambda: step_resident(nat.FLAG_NO_PRUNE), bsteps, 1)
         brute = (ms_b / bsteps, knn_b / bsteps, pairs_b / bsteps, last["value"])
 
+    clocks = sampler.stop() if sampler else None      # sampled across every timed leg above
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -33,8 +33,23 @@ def _coords(*groups) -> np.ndarray:
 
 
 def _classes(y):
-    """np.unique labels -> (int32 class id per row, number of classes, class sizes)."""
-    labels, inverse, sizes = np.unique(np.asarray(y), return_inverse=True, return_counts=True)
+    """np.unique labels -> (int32 class id per row, number of classes, class sizes).
+
+    Integer / boolean labels spanning a small range take a counting path (O(n), no sort) that yields
+    exactly what ``np.unique(y, return_inverse=True, return_counts=True)`` does: classes numbered in
+    ascending label order."""
+    y = np.asarray(y)
+    if y.ndim == 1 and y.dtype.kind in "iub" and y.size:
+        lo, hi = int(y.min()), int(y.max())
+        if hi - lo < (1 << 22):
+            shifted = (y.astype(np.int64) - lo) if y.dtype.kind != "b" else y.astype(np.int64)
+            if y.dtype.kind == "b":
+                lo = 0
+            hist = np.bincount(shifted, minlength=hi - lo + 1)
+            present = hist > 0
+            rank = np.cumsum(present) - 1                     # label value -> class id (ascending labels)
+            return np.ascontiguousarray(rank[shifted], dtype=np.int32), int(present.sum()), hist[present]
+    labels, inverse, sizes = np.unique(y, return_inverse=True, return_counts=True)
     return np.ascontiguousarray(np.ravel(inverse), dtype=np.int32), len(labels), sizes
 
 

@@ -238,3 +238,15 @@ def test_window_stats_bits():
             if len(view):
                 m, s = window_stats(view)
                 assert m == view.mean() and s == view.std()
+
+
+def test_class_ids_match_np_unique():
+    """The counting path for integer / boolean labels numbers classes exactly as np.unique does."""
+    from ennemi_b200._estimators import _classes
+    rng = np.random.default_rng(0)
+    for y in (rng.integers(0, 16, 5000), rng.integers(-5, 3, 1000), rng.integers(0, 2, 100).astype(bool), np.array([7, 7, 7]),
+              rng.integers(0, 200, 5000).astype(np.uint8), np.array(["a", "b", "a"]), rng.normal(size=50),
+              np.array([0, 2 ** 40, 5], dtype=np.int64)):
+        labels, inv, cnt = np.unique(y, return_inverse=True, return_counts=True)
+        c, n, sz = _classes(y)
+        assert n == len(labels) and np.array_equal(c, np.ravel(inv)) and np.array_equal(sz, cnt)

@@ -43,6 +43,8 @@ for flags in (0, nat.FLAG_NO_PRUNE, nat.FLAG_BRUTE_COUNT, nat.FLAG_NO_PRUNE | na
         if msgs:
             bad += 1; print("MISMATCH", n, "flags", flags, msgs)
 print("quick_parity: bad =", bad)
+if "--no-timing" in sys.argv:
+    sys.exit(1 if bad else 0)
 # a first timing: N=1e6 bivariate Gaussian
 rng = np.random.default_rng(0)
 for N in (100_000, 1_000_000):
