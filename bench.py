@@ -3,9 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one bivariate KSG estimate over the full 10^6-row synthetic Gaussian batch.  With N > 1
-(``torchrun``, one rank per GPU) the query rows of that one estimate are sharded over the ranks and
-the partial digamma sums are combined with one NCCL all-reduce ("strong" scaling: the work is fixed).
+A step is one bivariate KSG estimate over a full 10^6-row synthetic Gaussian batch per GPU.  The metric is
+a throughput, so with N > 1 (``torchrun``, one rank per GPU) independent same-shape estimates are fanned out,
+one per GPU per step, with no data-path collective ("weak" scaling; value = N estimates / max-over-ranks
+step time).  The other partition BASELINE.json configs[1] names — ONE estimate with its query rows sharded
+over the GPUs and one NCCL all-reduce of the partial digamma sums — is timed in the same run and reported
+under ``sharded``.
 
 Numbers on the JSON line:
   value      estimates/s with the coordinates already resident in HBM (C ABI, EB2_FLAG_DEVICE_INPUT)
@@ -31,6 +34,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "KSG MI estimates/sec at N=10^6, k=3"
 UNIT = "estimates/s"
@@ -44,8 +50,8 @@ SAMPLE_STRIDE = 50             # CPU baseline: every 50th row is queried, trees 
 NCU_DRAM_BYTES_PER_LAUNCH = 16.4e6
 
 
-def make_data(n=N_ROWS):
-    rng = np.random.default_rng(0)
+def make_data(n=N_ROWS, seed=0):
+    rng = np.random.default_rng(seed)
     d = rng.multivariate_normal([0, 0], [[1, RHO], [RHO, 1]], size=n)
     return np.ascontiguousarray(d[:, 1]), np.ascontiguousarray(d[:, 0])     # estimate_mi(d[:,1], d[:,0])
 
@@ -170,9 +176,17 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     ebd.enable_row_sharding(True)
 
+    # N = 1: the named batch.  N > 1: every rank gets its own batch of the same shape (seed = rank) for the
+    # task fan-out legs; rank 0's batch (replicated) is the one that is row-sharded in the `sharded` leg.
     y, x = make_data()
     xs, ys = preprocessed(y, x)
     coords_host = nat.pack_coords([xs, ys])
+    if world > 1:
+        y_own, x_own = make_data(seed=rank)
+        xs_own, ys_own = preprocessed(y_own, x_own)
+        coords_own = torch.from_numpy(nat.pack_coords([xs_own, ys_own])).to(dev)
+    else:
+        y_own, x_own = y, x
     coords_dev = torch.from_numpy(coords_host).to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
 
@@ -210,7 +224,8 @@ def run_gpu(args):
 
     last = {}
 
-    def step_resident(flags=0):
+    def step_sharded(flags=0):
+        """ONE estimate, query rows sharded over the ranks, one all-reduce of the partial block."""
         rank_, size_ = ebd.world()
         lo, hi = ebd.shard_bounds(N_ROWS, rank_, size_)
         part = nat.ksg_mi_rows(int(coords_dev.data_ptr()), N_ROWS, K_NEIGH, lo, hi, dev=local,
@@ -220,23 +235,35 @@ def run_gpu(args):
         last["value"] = nat.ksg_mi_finish(total, N_ROWS, K_NEIGH)
         return pairs
 
+    def step_fanout():
+        """One full estimate per rank on its own resident batch, no collective (task fan-out)."""
+        part = nat.ksg_mi_rows(int(coords_own.data_ptr()), N_ROWS, K_NEIGH, 0, N_ROWS, dev=local, flags=nat.FLAG_DEVICE_INPUT)
+        last["value_own"] = nat.ksg_mi_finish(part, N_ROWS, K_NEIGH)
+        return part[nat.P_PAIRS]
+
     def step_e2e():
-        last["e2e"] = float(eb.estimate_mi(y, x, k=K_NEIGH)[0, 0])
+        last["e2e"] = float(eb.estimate_mi(y_own, x_own, k=K_NEIGH)[0, 0])
         return None
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_res, launches, knn_ms, pairs = timed_steps(step_resident, args.steps, args.warmup)
-    ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
-
-    # task fan-out (weak scaling): every rank estimates its own resident batch per step, no collective
-    fan = None
-    if world > 1:
-        def step_fanout():
-            nat.ksg_mi_rows(int(coords_dev.data_ptr()), N_ROWS, K_NEIGH, 0, N_ROWS, dev=local, flags=nat.FLAG_DEVICE_INPUT)
-            return None
-        ms_f, _, _, _ = timed_steps(step_fanout, args.steps, 1)
-        fan = {"value": world * 1e3 / (ms_f / args.steps), "unit": UNIT, "scaling": "weak", "ms_per_step": ms_f / args.steps,
-               "note": "independent (pair / lag) tasks fanned out: one full N=1e6 estimate per rank per step, no collective"}
+    sharded = None
+    if world == 1:
+        ms_res, launches, knn_ms, pairs = timed_steps(step_sharded, args.steps, args.warmup)
+        ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
+    else:
+        # the metric is a throughput: on N GPUs independent estimates are fanned out, one per GPU per step
+        # (weak scaling, no data-path collective); the row-sharded single estimate of configs[1] is timed beside it
+        ebd.enable_row_sharding(False)
+        ms_res, launches, knn_ms, pairs = timed_steps(step_fanout, args.steps, args.warmup)
+        ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
+        ebd.enable_row_sharding(True)
+        ms_s, _, knn_s, _ = timed_steps(step_sharded, args.steps, args.warmup)
+        sharded = {"value": 1e3 / (ms_s / args.steps), "unit": UNIT, "scaling": "strong", "ms_per_step": ms_s / args.steps,
+                   "knn_ms": knn_s / args.steps, "mi": last["value"],
+                   "note": "configs[1]: ONE N=1e6 estimate, query rows sharded over the GPUs (full point set on every GPU), "
+                           "one NCCL all-reduce of the 8-double partial block; latency of a single estimate, bounded below by "
+                           "the per-rank sort/layout"}
+    units = world          # estimates per step
 
     # second half of BASELINE.json's metric: pairwise_mi wall time, 64 variables x N = 100,000 (configs[3]),
     # through the public API on host arrays; with N > 1 the 2,016 pair tasks are dealt over the ranks
@@ -267,7 +294,7 @@ def run_gpu(args):
     brute = None
     if world == 1 and not args.no_brute:
         bsteps = max(2, min(args.steps, 3))
-        ms_b, _, knn_b, pairs_b = timed_steps(lambda: step_resident(nat.FLAG_NO_PRUNE), bsteps, 1)
+        ms_b, _, knn_b, pairs_b = timed_steps(lambda: step_sharded(nat.FLAG_NO_PRUNE), bsteps, 1)
         brute = (ms_b / bsteps, knn_b / bsteps, pairs_b / bsteps, last["value"])
 
     clocks = sampler.stop() if sampler else None      # sampled across every timed leg above
@@ -282,24 +309,26 @@ def run_gpu(args):
     ops = pairs / args.steps * FP64_OPS_PER_PAIR                            # this rank's shard
     achieved = ops / (knn_per_ms * 1e-3) * 1e-12
     line = {
-        "metric": METRIC, "value": 1e3 / per_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": units * 1e3 / per_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]), "
-                               "query rows sharded over the GPUs, one all-reduce of the partial sums",
+        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]); a step = one "
+                               "estimate per GPU (N > 1: independent same-shape batches fanned out, no collective; the "
+                               "row-sharded single estimate is in `sharded`)",
                    "n": N_ROWS, "k": K_NEIGH, "algorithm": "exact two-level windowed all-pairs search (bit-exact eps and counts); brute force in brute_force",
                    "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
-                   "parallelism": f"rows/{world}"},
-        "mi": last["value"],
-        "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                   "parallelism": "single GPU" if world == 1 else f"task fan-out x{world} (+ rows/{world} in `sharded`)"},
+        "mi": last["value"] if world == 1 else last["value_own"],
+        "e2e": {"value": units * 1e3 / (ms_e2e / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(coords_host.nbytes), "d2h_bytes_per_step": 44,
-                "api": "ennemi_b200.estimate_mi(y, x, k=3) on host numpy arrays (host rescale+noise included)",
+                "api": "ennemi_b200.estimate_mi(y, x, k=3) on host numpy arrays (upload, rescale+noise, estimate, result read-back)"
+                       + ("" if world == 1 else "; one call per rank per step on its own arrays"),
                 "mi": last.get("e2e")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
-                     "survey_8d_frac": (float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR / world) / (knn_per_ms * 1e-3) * 1e-12 / peak,
+                     "survey_8d_frac": (float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR) / (knn_per_ms * 1e-3) * 1e-12 / peak,
                      "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
                              "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
                              "ops = pairs actually evaluated x 4 (k-NN main + leftover kernels, ms_per_launch = both); the pruned search is "
@@ -308,8 +337,8 @@ def run_gpu(args):
                              "in brute_force"},
         "clocks": clocks,
     }
-    if fan:
-        line["fanout"] = fan
+    if sharded:
+        line["sharded"] = sharded
     if pairwise:
         line["pairwise"] = pairwise
     if brute:
