@@ -708,21 +708,34 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
         const double lo_v = (q[1] - gate) - (fabs(q[1]) + gate) * slack;
         const double hi_v = (q[1] + gate) + (fabs(q[1]) + gate) * slack;
         const int nr = r_hi - r_lo, nl = l_hi - l_lo;
-        for (int idx = warp; idx < nr + nl; idx += NW) {
-          const int c = idx < nr ? r_lo + idx : l_lo + (idx - nr);
-          const int base = c * TCL;
-          const int lenv = min(TCL, le.c_len - base);
-          const double* yrow = a.P + a.rows.row[1] * a.stride + le.c_lo + base;
-          const int wlo = warp_first_true(0, lenv, [&](int sidx_) { return yrow[sidx_] >= lo_v; });
-          const int whi = warp_first_true(wlo, lenv, [&](int sidx_) { return yrow[sidx_] > hi_v; });
-          for (int j = wlo + lane; j < whi; j += 32) {
-            double c_[D];
-#pragma unroll
-            for (int t = 0; t < D; ++t) c_[t] = a.P[a.rows.row[t] * a.stride + le.c_lo + base + j];
-            const double m = cheb<D>(q, c_);
-            if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
+        // batches of 32 chunks per warp: every lane binary-searches the coordinate-1 window of ITS chunk (the
+        // 32 searches overlap their L2 latency), then the warp walks the non-empty windows together
+        for (int b0 = warp * 32; b0 < nr + nl; b0 += NW * 32) {
+          const int idx = b0 + lane;
+          int wlo = 0, whi = 0, base = 0;
+          if (idx < nr + nl) {
+            const int c = idx < nr ? r_lo + idx : l_lo + (idx - nr);
+            base = c * TCL;
+            const int lenv = min(TCL, le.c_len - base);
+            const double* yrow = a.P + a.rows.row[1] * a.stride + le.c_lo + base;
+            wlo = lower_bound_ge(yrow, lenv, lo_v);
+            whi = upper_bound_gt(yrow, lenv, hi_v);
           }
-          if (lane == 0) npairs += (unsigned long long)(whi - wlo);
+          unsigned int todo = __ballot_sync(0xffffffffu, wlo < whi);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int slo = __shfl_sync(0xffffffffu, wlo, src), shi = __shfl_sync(0xffffffffu, whi, src);
+            const int sbase = __shfl_sync(0xffffffffu, base, src);
+            for (int j = slo + lane; j < shi; j += 32) {
+              double c_[D];
+#pragma unroll
+              for (int t = 0; t < D; ++t) c_[t] = a.P[a.rows.row[t] * a.stride + le.c_lo + sbase + j];
+              const double m = cheb<D>(q, c_);
+              if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
+            }
+            if (lane == 0) npairs += (unsigned long long)(shi - slo);
+          }
         }
       }
     } else {
