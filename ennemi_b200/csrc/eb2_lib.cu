@@ -6,10 +6,16 @@
 //                           with NaN; rows of one class form a segment that starts on a 16-slot
 //                           boundary (TMA bulk copies need 16 B alignment); inside a segment the
 //                           rows are ascending in one chosen coordinate (`sort_row`), which is what
-//                           lets the all-pairs kernels skip candidate chunks exactly
+//                           lets the all-pairs kernels skip candidate chunks exactly.  Single-segment
+//                           sets of 2+ dimensions use the two-level layout: ascending in `sort_row`
+//                           ACROSS chunks of chunk_len(d) slots, ascending in a second coordinate
+//                           INSIDE each chunk (cell_sort_kernel), with the per-chunk range of
+//                           `sort_row` in cell_lo / cell_hi
 //   slot_row  stride        slot -> caller's row (-1 for padding)
 //   eps, radius, counts     per slot
-//   tiles                   one entry per 512-row query tile: query slots + candidate segment
+//   tiles                   one entry per 256- or 512-row query tile: query slots + candidate segment
+//   cache / derived         per device, across calls: uploaded columns, noise vectors and prepared
+//                           (rescaled + sorted) variables shared by the tasks of a call
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -409,7 +415,8 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
     if (!a.cell_lo) throw CudaFail{cudaErrorInvalidValue, "cell layout does not match the search space", __LINE__};
   } else if (ps.cell_lo) {
     throw CudaFail{cudaErrorInvalidValue, "cell layout used with a different search space", __LINE__};
-  } a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
+  }
+  a.eps = eps; a.heap = nullptr; a.pairs = pairs; a.ntiles = ts.count;
   a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
   const int k1t = (k + 1 <= 4) ? 4 : 8;
   if (a.sort_row >= 0 && k + 1 <= 8) {
