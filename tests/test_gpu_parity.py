@@ -219,3 +219,75 @@ def test_full_size_other_configs():
     want = oracle.knn_entropy(x4, 5, backend="scipy")
     value, parts = nat.entropy(nat.pack_coords([x4]), 5, details=True)
     assert np.array_equal(parts["dist"], want["dist"]) and close(value, want["value"])
+
+
+@pytest.mark.parametrize("n", [2, 5, 16, 17, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2049])
+def test_tile_and_chunk_boundary_sizes(n):
+    """Sizes around the 16-slot padding, the 256/512-row tiles and the 512-slot chunks, for the 2-D
+    (two-level), 1-D (one-level) and 5-D paths, pruned and brute force."""
+    import oracle
+    rng = np.random.default_rng(n)
+    k = min(3, n - 1)
+    x = rng.normal(size=n); y = 0.5 * x + rng.normal(size=n)
+    want = oracle.ksg_mi(x, y, k, backend="c")
+    for flags in (0, nat.FLAG_NO_PRUNE):
+        value, parts = nat.ksg_mi(nat.pack_coords([x, y]), k, flags=flags, details=True)
+        assert all(np.array_equal(parts[key], want[key]) for key in ("eps", "nx", "ny")), (n, flags)
+        assert close(value, want["value"])
+    assert np.array_equal(nat.entropy(nat.pack_coords([x]), k, details=True)[1]["dist"], oracle.kth_distance(x, k, backend="c"))
+    if n > 4:
+        z = rng.normal(size=(n, 3))
+        wc = oracle.conditional_mi(x, y, z, k, backend="c")
+        vc, pc = nat.cmi(nat.pack_coords([x, y, z]), k, details=True)
+        assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"])
+
+
+@pytest.mark.parametrize("kind", ["cauchy", "outlier", "x_ties", "clusters", "lattice", "sorted_input"])
+def test_hard_distributions(kind):
+    """Data that stress the pruning: heavy tails and a far outlier (wide windows, deferred stragglers), ties
+    in the sort coordinate, tight clusters, a lattice with many exact ties in both coordinates, presorted rows."""
+    import oracle
+    rng = np.random.default_rng(len(kind))
+    n = 6_000
+    if kind == "cauchy":
+        x = rng.standard_cauchy(n); y = x + rng.standard_cauchy(n)
+    elif kind == "outlier":
+        x = rng.normal(size=n); y = rng.normal(size=n); x[7] = 1e6; y[11] = -1e7
+    elif kind == "x_ties":
+        x = rng.integers(0, 20, n).astype(float); y = rng.normal(size=n) + 0.1 * x
+    elif kind == "clusters":
+        c = rng.integers(0, 5, n); x = c * 100.0 + rng.normal(size=n) * 1e-3; y = c * -50.0 + rng.normal(size=n) * 1e-3
+    elif kind == "lattice":
+        x = rng.integers(0, 40, n).astype(float); y = rng.integers(0, 40, n).astype(float)
+    else:
+        x = np.sort(rng.normal(size=n)); y = np.sort(rng.normal(size=n))[::-1].copy()
+    for k in (1, 3, 20):
+        want = oracle.ksg_mi(x, y, k, backend="c")
+        value, parts = nat.ksg_mi(nat.pack_coords([x, y]), k, details=True)
+        for key in ("eps", "nx", "ny"):
+            assert np.array_equal(parts[key], want[key]), (kind, k, key, int(np.sum(parts[key] != want[key])))
+        assert close(value, want["value"]), (kind, k, value, want["value"])
+    z = np.column_stack((y, x * 0.5 + rng.normal(size=n)))
+    wc = oracle.conditional_mi(x, y, z, 3, backend="c")
+    vc, pc = nat.cmi(nat.pack_coords([x, y, z]), 3, details=True)
+    assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"]), kind
+
+
+def test_ragged_classes():
+    """Ross estimators with classes of size 1, k, k+1 and one big class; class ids in arbitrary row order."""
+    import oracle
+    rng = np.random.default_rng(3)
+    sizes = [1, 3, 4, 5, 16, 17, 600, 2000]
+    y = np.repeat(np.arange(len(sizes)), sizes); rng.shuffle(y)
+    n = len(y)
+    x = rng.normal(size=n) + 0.3 * y; z = rng.normal(size=(n, 2))
+    cls, ncls = classes(y)
+    for k in (3, 4):
+        w = oracle.semidiscrete_mi(x, y, k, backend="c")
+        v, p = nat.ross_mi(nat.pack_coords([x]), cls, ncls, k, details=True)
+        assert np.array_equal(p["eps"], w["eps"]) and np.array_equal(p["n_full"], w["n_full"]) and close(v, w["value"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            wc = oracle.conditional_semidiscrete_mi(x, y, z, k, backend="c")
+        vc, pc = nat.ross_cmi(nat.pack_coords([x, z]), cls, ncls, k, details=True)
+        assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"])
