@@ -92,6 +92,8 @@ struct Ctx {
   bool ready = false;
   std::mutex mu;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // second stream: work that can overlap the k-NN kernel (marginal sort)
+  cudaEvent_t fork = nullptr, join = nullptr;
   cudaEvent_t ev[kNumEvents] = {};
   int sm_count = 148;
   char* pinned = nullptr;   // host staging: tile tables up, results down
@@ -116,6 +118,9 @@ Ctx& get_ctx(int dev_lane) {
   if (dev >= count) throw CudaFail{cudaErrorInvalidDevice, "device index beyond cudaGetDeviceCount", __LINE__};
   CU(cudaSetDevice(dev));
   CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming));
   for (auto& e : c.ev) CU(cudaEventCreate(&e));
   CU(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
   cudaMemPool_t pool;
@@ -151,7 +156,12 @@ struct Scratch {
   int launches = 0;
   explicit Scratch(Ctx& ctx) : c(ctx) {}
   std::vector<void*> extra_pinned;
+  bool used_side = false;     // work was forked to the second stream: it must finish before buffers are released
   ~Scratch() {
+    if (used_side) {
+      cudaEventRecord(c.join, c.side);
+      cudaStreamWaitEvent(c.stream, c.join, 0);
+    }
     for (void* p : ptrs) cudaFreeAsync(p, c.stream);
     if (!extra_pinned.empty()) {
       cudaStreamSynchronize(c.stream);
@@ -825,6 +835,8 @@ int eb2_shutdown(void) {
     }
     cudaStreamSynchronize(c.stream);
     for (auto& e : c.ev) cudaEventDestroy(e);
+    cudaEventDestroy(c.fork); cudaEventDestroy(c.join);
+    cudaStreamDestroy(c.side);
     cudaStreamDestroy(c.stream);
     cudaFreeHost(c.pinned);
     c.pinned = nullptr;
@@ -987,6 +999,23 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
       ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
     }
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
+    // the ascending y needed by the n_y search does not depend on the k-NN pass: sort it on the second
+    // stream while the k-NN kernel runs (the sort kernels fill the SM time the k-NN tail leaves idle)
+    const double* ys = dy ? dy->sorted : nullptr;
+    bool forked = false;
+    if (!ys && !(flags & EB2_FLAG_BRUTE_COUNT)) {
+      double* t = s.dev<double>(n);
+      size_t tmp_bytes = 0;
+      CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, raw + n, t, (int)n, 0, 64, c.side));
+      void* tmp = s.dev<char>(tmp_bytes);
+      s.used_side = true;
+      CU(cudaEventRecord(c.fork, c.stream));
+      CU(cudaStreamWaitEvent(c.side, c.fork, 0));
+      CU(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, raw + n, t, (int)n, 0, 64, c.side));
+      CU(cudaEventRecord(c.join, c.side));
+      ys = t;
+      forked = true;
+    }
     mark(s, 1);
     double* eps = s.dev<double>(ps.stride);
     double* radius = s.dev<double>(ps.stride);
@@ -994,6 +1023,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     mark(s, 2);
     radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
     s.launches++;
+    if (forked) CU(cudaStreamWaitEvent(c.stream, c.join, 0));
     int* nx = s.dev<int>(ps.stride);
     int* ny = s.dev<int>(ps.stride);
     if (flags & EB2_FLAG_BRUTE_COUNT) {
@@ -1002,8 +1032,6 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     } else {
       const double* xs = ps.sorted_keys;             // x in ascending order, by-product of the layout sort
       if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
-      const double* ys = dy ? dy->sorted : nullptr;
-      if (!ys) { double* t = s.dev<double>(n); sort_keys(s, raw + n, t, (int)n); ys = t; }
       TileSet all = make_tiles(s, ps, row_lo, row_hi, false, 0, (int)n);
       run_search(s, ps.P, radius, xs, all, nx);
       run_search(s, ps.P + ps.stride, radius, ys, all, ny);
