@@ -13,7 +13,13 @@ __host__ __device__ constexpr int tile_rows(int qpt) { return kThreads * qpt; }
 constexpr int kSegAlign = 16;      // segments start on 16-slot (128 B) boundaries: TMA bulk copies need 16 B
 
 // Candidate-chunk length (slots) staged in shared memory per step, by dimension of the space.
-__host__ __device__ constexpr int chunk_len(int d) { return d <= 5 ? 512 : (d <= 8 ? 256 : 128); }
+#ifndef EB2_CHUNK2
+#define EB2_CHUNK2 2048
+#endif
+#ifndef EB2_CHUNK5
+#define EB2_CHUNK5 1024
+#endif
+__host__ __device__ constexpr int chunk_len(int d) { return d <= 2 ? EB2_CHUNK2 : (d <= 5 ? EB2_CHUNK5 : (d <= 8 ? 256 : 128)); }
 
 // One tile of query rows and the candidate segment it is compared against.
 struct Tile {

@@ -165,15 +165,15 @@ __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
   const int tid = threadIdx.x;
   for (int k = 2; k <= NQ; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (tid < NQ / 2) {
-      const int i = 2 * j * (tid / j) + (tid % j);
-      const int l = i + j;
-      const bool up = (i & k) == 0;
-      const double a = skey[i], b = skey[l];
-      if ((a > b) == up) {
-        skey[i] = b; skey[l] = a;
-        const int t = sidx[i]; sidx[i] = sidx[l]; sidx[l] = t;
-      }
+      for (int p = tid; p < NQ / 2; p += kThreads) {     // NQ/2 compare-exchanges per stage
+        const int i = 2 * j * (p / j) + (p % j);
+        const int l = i + j;
+        const bool up = (i & k) == 0;
+        const double a = skey[i], b = skey[l];
+        if ((a > b) == up) {
+          skey[i] = b; skey[l] = a;
+          const int t = sidx[i]; sidx[i] = sidx[l]; sidx[l] = t;
+        }
       }
       __syncthreads();
     }
