@@ -213,6 +213,7 @@ def run_gpu(args):
             t = nat.last_timing(local)
             launches += t["launches"]
             knn_ms += t["knn_ms"]
+            last["phases"] = t
             if extra is not None:
                 pairs += extra
         barrier()
@@ -249,12 +250,14 @@ def run_gpu(args):
     sharded = None
     if world == 1:
         ms_res, launches, knn_ms, pairs = timed_steps(step_sharded, args.steps, args.warmup)
+        phases = dict(last["phases"])
         ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
     else:
         # the metric is a throughput: on N GPUs independent estimates are fanned out, one per GPU per step
         # (weak scaling, no data-path collective); the row-sharded single estimate of configs[1] is timed beside it
         ebd.enable_row_sharding(False)
         ms_res, launches, knn_ms, pairs = timed_steps(step_fanout, args.steps, args.warmup)
+        phases = dict(last["phases"])
         ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
         ebd.enable_row_sharding(True)
         ms_s, _, knn_s, _ = timed_steps(step_sharded, args.steps, args.warmup)
@@ -325,6 +328,7 @@ def run_gpu(args):
                        + ("" if world == 1 else "; one call per rank per step on its own arrays"),
                 "mi": last.get("e2e")},
         "gpu_launches": int(launches),
+        "phase_ms": phases,
         "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,

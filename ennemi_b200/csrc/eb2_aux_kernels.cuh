@@ -14,18 +14,26 @@ struct SearchArgs {
   const double* qcoord;   // query coordinate per query slot
   const double* radius;   // per query slot
   const double* sorted;   // ascending candidate coordinates
+  // optional second marginal searched by the same launch (blockIdx.y == 1)
+  const double* qcoord2;
+  const double* sorted2;
+  int* cnt2;
   const Tile* tiles;      // q_lo/q_n: query slots; c_lo/c_len: slice of `sorted` to search
   int ntiles;
   int* cnt;               // out per query slot
 };
 
 __global__ void __launch_bounds__(kThreads) search_kernel(const SearchArgs a) {
+  const bool second = blockIdx.y == 1;
+  const double* qcoord = second ? a.qcoord2 : a.qcoord;
+  const double* sorted = second ? a.sorted2 : a.sorted;
+  int* cnt = second ? a.cnt2 : a.cnt;
   for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = a.tiles[tile_id];
-    const double* s = a.sorted + tile.c_lo;
+    const double* s = sorted + tile.c_lo;
     for (int qi = threadIdx.x; qi < tile.q_n; qi += kThreads) {
       const int slot = tile.q_lo + qi;
-      const double x = a.qcoord[slot];
+      const double x = qcoord[slot];
       const double r = a.radius[slot];
       // first j with fl(x - s_j) <= r   (x - s_j is non-increasing in j)
       int lo = 0, hi = tile.c_len;
@@ -40,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchArgs a) {
         const int mid = (lo + hi) >> 1;
         if ((s[mid] - x) > r) hi = mid; else lo = mid + 1;
       }
-      a.cnt[slot] = max(0, lo - first);
+      cnt[slot] = max(0, lo - first);
     }
   }
 }

@@ -165,7 +165,7 @@ __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
   const int tid = threadIdx.x;
   for (int k = 2; k <= NQ; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = tid; p < NQ / 2; p += kThreads) {     // NQ/2 compare-exchanges per stage
+      for (int p = tid; p < NQ / 2; p += blockDim.x) {   // NQ/2 compare-exchanges per stage
         const int i = 2 * j * (p / j) + (p % j);
         const int l = i + j;
         const bool up = (i & k) == 0;
@@ -196,7 +196,7 @@ __device__ __forceinline__ void cta_permute(double* xch, const int (&src)[QPT], 
 // range of row1 in it (cell_lo / cell_hi) and reorders the chunk's slots by `row2` (bitonic sort in
 // shared memory); all d rows and slot_row are permuted alike.  NaN padding sorts last.
 template <int TC>
-__global__ void __launch_bounds__(kThreads) cell_sort_kernel(double* P, int64_t stride, int d, int* slot_row, int64_t n,
+__global__ void __launch_bounds__((TC / 2 < 1024 ? (TC / 2 < 256 ? 256 : TC / 2) : 1024)) cell_sort_kernel(double* P, int64_t stride, int d, int* slot_row, int64_t n,
                                                             int row1, int row2, double* cell_lo, double* cell_hi) {
   __shared__ __align__(16) double skey[TC];
   __shared__ int sidx[TC];
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) cell_sort_kernel(double* P, int64_t 
     cell_hi[blockIdx.x] = P[row1 * stride + base + nvalid - 1];
   }
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-  for (int i = tid; i < TC; i += kThreads) {
+  for (int i = tid; i < TC; i += blockDim.x) {
     const double v = (i < nvalid) ? P[row2 * stride + base + i] : kInf;   // padding sorts last
     skey[i] = (v == v) ? v : kInf;
     sidx[i] = i;
@@ -220,15 +220,15 @@ __global__ void __launch_bounds__(kThreads) cell_sort_kernel(double* P, int64_t 
   const int nslots = (int)min((int64_t)TC, stride - base);
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
   for (int t = 0; t < d; ++t) {
-    for (int i = tid; i < nvalid; i += kThreads) sval[i] = P[t * stride + base + i];
+    for (int i = tid; i < nvalid; i += blockDim.x) sval[i] = P[t * stride + base + i];
     __syncthreads();
-    for (int i = tid; i < nslots; i += kThreads) P[t * stride + base + i] = (i < nvalid) ? sval[sidx[i]] : kNaN;
+    for (int i = tid; i < nslots; i += blockDim.x) P[t * stride + base + i] = (i < nvalid) ? sval[sidx[i]] : kNaN;
     __syncthreads();
   }
   int* ival = reinterpret_cast<int*>(sval);
-  for (int i = tid; i < nvalid; i += kThreads) ival[i] = slot_row[base + i];
+  for (int i = tid; i < nvalid; i += blockDim.x) ival[i] = slot_row[base + i];
   __syncthreads();
-  for (int i = tid; i < nslots; i += kThreads) slot_row[base + i] = (i < nvalid) ? ival[sidx[i]] : -1;
+  for (int i = tid; i < nslots; i += blockDim.x) slot_row[base + i] = (i < nvalid) ? ival[sidx[i]] : -1;
 }
 
 // candidates tested per branch in the all-pairs inner loops (register budget: 2*G*D for the group)

@@ -70,8 +70,8 @@ cudaError_t launch_knn(int D, int qpt, const KnnArgs& a, int grid, cudaStream_t 
 cudaError_t launch_cell_sort(int D, double* P, int64_t stride, int d, int* slot_row, int64_t n, int row1, int row2,
                              double* cell_lo, double* cell_hi, int nchunks, cudaStream_t s) {
   switch (chunk_len(D)) {
-    case 2048: cell_sort_kernel<2048><<<nchunks, kThreads, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
-    case 1024: cell_sort_kernel<1024><<<nchunks, kThreads, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
+    case 2048: cell_sort_kernel<2048><<<nchunks, 1024, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
+    case 1024: cell_sort_kernel<1024><<<nchunks, 512, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
     case 512: cell_sort_kernel<512><<<nchunks, kThreads, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
     case 256: cell_sort_kernel<256><<<nchunks, kThreads, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;
     case 128: cell_sort_kernel<128><<<nchunks, kThreads, 0, s>>>(P, stride, d, slot_row, n, row1, row2, cell_lo, cell_hi); break;

@@ -502,11 +502,14 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
   s.launches++;
 }
 
-void run_search(Scratch& s, const double* qcoord, const double* radius, const double* sorted, const TileSet& ts, int* cnt) {
+// one or (qcoord2 != NULL) two 1-D marginals searched by one launch
+void run_search(Scratch& s, const double* qcoord, const double* radius, const double* sorted, const TileSet& ts, int* cnt,
+                const double* qcoord2 = nullptr, const double* sorted2 = nullptr, int* cnt2 = nullptr) {
   if (!ts.count) return;
   SearchArgs a;
   a.qcoord = qcoord; a.radius = radius; a.sorted = sorted; a.tiles = ts.dev; a.ntiles = ts.count; a.cnt = cnt;
-  search_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(a);
+  a.qcoord2 = qcoord2; a.sorted2 = sorted2; a.cnt2 = cnt2;
+  search_kernel<<<dim3(ts.count, qcoord2 ? 2 : 1), kThreads, 0, s.c.stream>>>(a);
   CU(cudaGetLastError());
   s.launches++;
 }
@@ -1033,8 +1036,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
       const double* xs = ps.sorted_keys;             // x in ascending order, by-product of the layout sort
       if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
       TileSet all = make_tiles(s, ps, row_lo, row_hi, false, 0, (int)n);
-      run_search(s, ps.P, radius, xs, all, nx);
-      run_search(s, ps.P + ps.stride, radius, ys, all, ny);
+      run_search(s, ps.P, radius, xs, all, nx, ps.P + ps.stride, ys, ny);
     }
     mark(s, 3);
     double* out4 = run_psi(s, PSI_AB, nx, ny, nullptr, nullptr, self);
