@@ -151,13 +151,14 @@ class ColsTask:
     """A continuous (x, y[, cond]) task on cached columns; ``run()`` returns the estimate."""
 
     __slots__ = ("store", "xkey", "ykey", "zkeys", "xview", "yview", "cond", "lag", "hi", "lo", "cond_lag", "k",
-                 "preprocess", "n_total")
+                 "preprocess", "n_total", "single_use")
 
     def __init__(self, store, xkey, ykey, zkeys, xview, yview, cond, lag, hi, lo, cond_lag, k, preprocess):
         self.store, self.xkey, self.ykey, self.zkeys = store, xkey, ykey, zkeys
         self.xview, self.yview, self.cond = xview, yview, cond
         self.lag, self.hi, self.lo, self.cond_lag, self.k, self.preprocess = lag, hi, lo, cond_lag, k, preprocess
         self.n_total = len(yview)
+        self.single_use = False      # set by the API when the call consists of this one task
 
     def describe(self, dev: int):
         """(descriptors, n) of this task for device ``dev``: uploads what is missing, computes (cached)
@@ -252,9 +253,10 @@ class ColsTask:
                 if self.zkeys:
                     return _native.cmi_finish(part, n, self.k)
                 return _native.ksg_mi_finish(part, n, self.k)
+            flags = _native.FLAG_SINGLE_USE if self.single_use else 0
             if self.zkeys:
-                return _native.cmi_cols(descs, n, self.k, dev=dev)
-            return _native.ksg_mi_cols(descs, n, self.k, dev=dev)
+                return _native.cmi_cols(descs, n, self.k, dev=dev, flags=flags)
+            return _native.ksg_mi_cols(descs, n, self.k, dev=dev, flags=flags)
         except _native.NonFiniteInput as e:
             if e.nan:
                 raise ValueError(_checks.MSG_NANS_LEFT) from None

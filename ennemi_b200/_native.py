@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libennemi_b200.so")
 FLAG_DEVICE_INPUT = 1
 FLAG_BRUTE_COUNT = 2
 FLAG_NO_PRUNE = 4
+FLAG_SINGLE_USE = 8
 
 ERR_CUDA, ERR_ARG, ERR_NONFINITE, ERR_UNSUPPORTED = 1, 2, 3, 4
 P_LEN = 8

@@ -211,6 +211,8 @@ def estimate_mi(y, x, lag=0, *, k: int = 3, cond=None, cond_lag=0, mask=None,
         zkeys = [] if cond_arr is None else [store.add(cond_arr[:, j]) for j in range(n_cond)]
         tasks = [ColsTask(store, xkeys[v], ykey, zkeys, x_cols[v], y_arr, cond_arr, lags[li], hi, lo, cond_lags[li],
                           k, preprocess) for li, v in cells]
+        if len(tasks) == 1:
+            tasks[0].single_use = True
     else:
         tasks = [MiTask(x_cols[v], y_arr, lags[li], hi, lo, k, mask_arr, cond_arr,
                         cond_lags[li], discrete_x, discrete_y, preprocess, drop_nan) for li, v in cells]

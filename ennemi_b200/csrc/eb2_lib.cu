@@ -988,7 +988,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     const Derived* dx = nullptr;
     const Derived* dy = nullptr;
     PointSet ps;
-    if (in.cols && prune && !(flags & EB2_FLAG_BRUTE_COUNT) && !getenv("EB2_NO_DERIVED")) {
+    if (in.cols && prune && !(flags & (EB2_FLAG_BRUTE_COUNT | EB2_FLAG_SINGLE_USE)) && !getenv("EB2_NO_DERIVED")) {
       // prepared variables (rescaled values + their ascending order) are shared by all tasks of the call
       dx = get_derived(s, in.cols[0], n);
       dy = get_derived(s, in.cols[1], n);

@@ -54,6 +54,7 @@ extern "C" {
 #define EB2_FLAG_DEVICE_INPUT 1u /* coords / cls are device pointers on `dev` */
 #define EB2_FLAG_BRUTE_COUNT 2u  /* count 1-D marginals with the tiled all-pairs kernel instead of sort+search */
 #define EB2_FLAG_NO_PRUNE 4u     /* visit every candidate tile (pure brute force); default is exact sorted-window pruning */
+#define EB2_FLAG_SINGLE_USE 8u   /* *_cols calls: the descriptors are used by this task only - do not cache prepared variables */
 
 /* layout of the 8-double partial block */
 #define EB2_P_SUM 0   /* sum over rows of the per-row term (psi combination, or log(dist)) */
