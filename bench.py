@@ -55,6 +55,9 @@ def make_data(n=N_ROWS, seed=0):
     return np.ascontiguousarray(d[:, 1]), np.ascontiguousarray(d[:, 0])     # estimate_mi(d[:,1], d[:,0])
 
 
+_orig_make_data = make_data
+
+
 def preprocessed(y, x):
     """The buffers the estimator sees inside estimate_mi(y, x): rescaled + fixed-seed noise."""
     from ennemi_b200 import _align
