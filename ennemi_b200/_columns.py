@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import itertools
 import threading
+import time
 import warnings
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
@@ -56,29 +57,37 @@ def window_stats(view: np.ndarray) -> Tuple[float, float]:
 
 class NoiseBank:
     """The reference's fixed-seed noise draws (``_driver.py:874,883``), memoised on the host by
-    ``_align._NoiseStream`` and mirrored on each GPU under a cache key."""
+    ``_align._NoiseStream`` and mirrored on each GPU under a cache key.  Least-recently-used entries are
+    dropped from the devices once more than ``MAX_ENTRIES`` draw sequences are live, but never while they
+    may still be referenced by a running task (entries used within the last ``MIN_AGE_S`` seconds stay)."""
 
     _lock = threading.Lock()
-    _keys: "OrderedDict[tuple, int]" = OrderedDict()        # draw-shape sequence -> cache key
+    _keys: "OrderedDict[tuple, list]" = OrderedDict()       # draw-shape sequence -> [cache key, last use]
     _on_device: Dict[int, set] = {}
     MAX_ENTRIES = 64
+    MIN_AGE_S = 120.0
 
     @classmethod
     def key_for(cls, shapes: tuple, values: np.ndarray, dev: int) -> int:
         ordinal = _devices.ordinal(dev)
+        now = time.monotonic()
         with cls._lock:
-            key = cls._keys.get(shapes)
-            if key is None:
-                key = _new_key()
-                cls._keys[shapes] = key
+            entry = cls._keys.get(shapes)
+            if entry is None:
+                entry = cls._keys[shapes] = [_new_key(), now]
                 while len(cls._keys) > cls.MAX_ENTRIES:
-                    _, old = cls._keys.popitem(last=False)
+                    oldest = next(iter(cls._keys))
+                    if now - cls._keys[oldest][1] < cls.MIN_AGE_S:
+                        break
+                    old = cls._keys.pop(oldest)[0]
                     for d, have in cls._on_device.items():
                         if old in have:
                             have.discard(old)
                             _native.cache_drop(old, dev=d)
             else:
+                entry[1] = now
                 cls._keys.move_to_end(shapes)
+            key = entry[0]
             have = cls._on_device.setdefault(ordinal, set())
             if key not in have:
                 _native.cache_put(key, np.ravel(values), dev=dev)

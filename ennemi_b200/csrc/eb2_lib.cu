@@ -620,20 +620,29 @@ Derived* get_derived(Scratch& s, const eb2_col_t& col, int64_t n) {
     Derived d;
     cudaStream_t st = s.c.stream;
     d.n = n; d.src_key = col.key; d.noise_key = col.nkey;
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.vals), sizeof(double) * n, st));
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.sorted), sizeof(double) * n, st));
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.perm), sizeof(int) * n, st));
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&d.dflag), sizeof(int), st));
-    CU(cudaMemsetAsync(d.dflag, 0, sizeof(int), st));
-    pa.raw = d.vals; pa.flags = d.dflag;
-    prep_kernel<<<cdiv(n, 256), 256, 0, st>>>(pa);
-    nonfinite_kernel<<<cdiv(n, 256), 256, 0, st>>>(d.vals, n, d.dflag);
-    int* iota = s.dev<int>(n);
-    iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, static_cast<int>(n));
-    s.launches += 3;
-    sort_pairs<double, int>(s, d.vals, d.sorted, iota, d.perm, static_cast<int>(n), 0, 64);
-    CU(cudaEventCreateWithFlags(&d.ready, cudaEventDisableTiming));
-    CU(cudaEventRecord(d.ready, st));
+    try {
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d.vals), sizeof(double) * n, st));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d.sorted), sizeof(double) * n, st));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d.perm), sizeof(int) * n, st));
+      CU(cudaMallocAsync(reinterpret_cast<void**>(&d.dflag), sizeof(int), st));
+      CU(cudaMemsetAsync(d.dflag, 0, sizeof(int), st));
+      pa.raw = d.vals; pa.flags = d.dflag;
+      prep_kernel<<<cdiv(n, 256), 256, 0, st>>>(pa);
+      nonfinite_kernel<<<cdiv(n, 256), 256, 0, st>>>(d.vals, n, d.dflag);
+      int* iota = s.dev<int>(n);
+      iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(iota, static_cast<int>(n));
+      s.launches += 3;
+      sort_pairs<double, int>(s, d.vals, d.sorted, iota, d.perm, static_cast<int>(n), 0, 64);
+      CU(cudaEventCreateWithFlags(&d.ready, cudaEventDisableTiming));
+      CU(cudaEventRecord(d.ready, st));
+    } catch (...) {        // nothing half-built stays behind
+      if (d.vals) cudaFreeAsync(d.vals, st);
+      if (d.sorted) cudaFreeAsync(d.sorted, st);
+      if (d.perm) cudaFreeAsync(d.perm, st);
+      if (d.dflag) cudaFreeAsync(d.dflag, st);
+      if (d.ready) cudaEventDestroy(d.ready);
+      throw;
+    }
     it = sh.derived.emplace(key, d).first;
   }
   CU(cudaStreamWaitEvent(s.c.stream, it->second.ready, 0));
