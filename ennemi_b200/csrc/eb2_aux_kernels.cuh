@@ -145,7 +145,7 @@ __global__ void iota_kernel(int* v, int n) {
 // rank -> padded slot.  Unsegmented: slot = rank.  Segmented: ranks are class-major, class c owns
 // ranks [seg_rank[c], seg_rank[c+1]) and slots starting at seg_slot[c].
 struct GatherArgs {
-  const double* rows[kMaxDim + 1];   // source of each of the d rows (n values, caller's row order)
+  const double* rows[kMaxDimAny + 1];   // source of each of the d rows (n values, caller's row order)
   int64_t n;
   int d;
   const int* perm;        // rank -> input row (NULL: identity)
@@ -211,7 +211,7 @@ struct PrepCol {
   long long noff, nstride;
 };
 struct PrepArgs {
-  PrepCol col[kMaxDim];
+  PrepCol col[kMaxDimAny];
   int d;
   long long n;
   double* raw;
@@ -332,6 +332,97 @@ __global__ void fp64_peak_kernel(double* out, double c, int iters) {
     a4 = __dadd_rn(a4, c); a5 = __dadd_rn(a5, c); a6 = __dadd_rn(a6, c); a7 = __dadd_rn(a7, c);
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ---- generic run-time-dimension brute-force kernels (spaces wider than kMaxDim) ----------------
+__global__ void __launch_bounds__(kThreads) knn_generic_kernel(const GenKnnArgs a) {
+  __shared__ double sbuf[kMaxDimAny * kGenChunk];
+  const int tid = threadIdx.x;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = a.tiles[tile_id];
+    const bool valid = tid < tile.q_n;
+    double q[kMaxDimAny];
+    for (int t = 0; t < a.d; ++t) q[t] = valid ? a.P[a.rows.row[t] * a.stride + tile.q_lo + tid] : kNaN;
+    HeapRef heap;
+    heap.nq = (int64_t)gridDim.x * kThreads;
+    heap.base = a.heap + (int64_t)blockIdx.x * kThreads + tid;
+    heap.k1 = a.k + 1;
+    heap.fill_inf();
+    double thr = kInf;
+    const int len_pad = (tile.c_len + kSegAlign - 1) / kSegAlign * kSegAlign;
+    for (int c0 = 0; c0 < len_pad; c0 += kGenChunk) {
+      const int len = min(kGenChunk, len_pad - c0);
+      for (int idx = tid; idx < a.d * len; idx += kThreads) {
+        const int t = idx / len, j = idx - t * len;
+        sbuf[t * kGenChunk + j] = a.P[a.rows.row[t] * a.stride + tile.c_lo + c0 + j];
+      }
+      __syncthreads();
+      for (int j = 0; j < len; ++j) {
+        bool in = true;
+        double m = 0.0;
+        for (int t = 0; t < a.d && in; ++t) {
+          const double v = fabs(q[t] - sbuf[t * kGenChunk + j]);
+          in = v < thr;                  // NaN padding fails here
+          m = v > m ? v : m;
+        }
+        if (in) thr = heap.replace_root(m);
+      }
+      __syncthreads();
+    }
+    if (valid) a.eps[tile.q_lo + tid] = thr;
+    if (tid == 0 && a.pairs) atomicAdd(a.pairs, (unsigned long long)tile.c_len * tile.q_n);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) count_generic_kernel(const GenCountArgs a) {
+  __shared__ double sbuf[(kMaxDimAny + 2) * kGenChunk];
+  const int tid = threadIdx.x;
+  const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+  const int D = a.C + a.E;
+  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = a.tiles[tile_id];
+    const bool valid = tid < tile.q_n;
+    const int slot = tile.q_lo + tid;
+    double qs[kMaxDimAny];
+    double qe[2] = {kNaN, kNaN};
+    for (int t = 0; t < a.C; ++t) qs[t] = valid ? a.Q[a.q_srow.row[t] * a.qstride + slot] : kNaN;
+    for (int t = 0; t < a.E; ++t) qe[t] = valid ? a.Q[a.q_erow.row[t] * a.qstride + slot] : kNaN;
+    const double r = valid ? a.radius[slot] : kNaN;
+    int ns = 0, ne0 = 0, ne1 = 0;
+    const int len_pad = (tile.c_len + kSegAlign - 1) / kSegAlign * kSegAlign;
+    for (int c0 = 0; c0 < len_pad; c0 += kGenChunk) {
+      const int len = min(kGenChunk, len_pad - c0);
+      for (int idx = tid; idx < D * len; idx += kThreads) {
+        const int t = idx / len, j = idx - t * len;
+        const int row = t < a.C ? a.b_srow.row[t] : a.b_erow.row[t - a.C];
+        sbuf[t * kGenChunk + j] = a.B[row * a.bstride + tile.c_lo + c0 + j];
+      }
+      __syncthreads();
+      for (int j = 0; j < len; ++j) {
+        bool in = true;
+        for (int t = 0; t < a.C && in; ++t) in = fabs(qs[t] - sbuf[t * kGenChunk + j]) <= r;
+        if (a.C > 0) {
+          if (in) {
+            ++ns;
+            if (a.E > 0) ne0 += (int)(fabs(qe[0] - sbuf[a.C * kGenChunk + j]) <= r);
+            if (a.E > 1) ne1 += (int)(fabs(qe[1] - sbuf[(a.C + 1) * kGenChunk + j]) <= r);
+          }
+        } else {
+          if (a.E > 0) ne0 += (int)(fabs(qe[0] - sbuf[j]) <= r);
+          if (a.E > 1) ne1 += (int)(fabs(qe[1] - sbuf[kGenChunk + j]) <= r);
+        }
+      }
+      __syncthreads();
+    }
+    if (valid) {
+      if (a.C > 0) a.cnt_s[slot] = ns;
+      if (a.E > 0) a.cnt_e0[slot] = ne0;
+      if (a.E > 1) a.cnt_e1[slot] = ne1;
+    }
+    if (tid == 0 && a.pairs) atomicAdd(a.pairs, (unsigned long long)tile.c_len * tile.q_n);
+  }
 }
 
 }  // namespace eb2

@@ -5,7 +5,8 @@
 
 namespace eb2 {
 
-constexpr int kMaxDim = 12;        // EB2_MAX_DIM
+constexpr int kMaxDim = 12;        // dimensions with specialised (register-resident) kernels
+constexpr int kMaxDimAny = 32;     // EB2_MAX_DIM: beyond kMaxDim a generic run-time-dimension brute-force path is used
 constexpr int kThreads = 256;      // threads per CTA in the all-pairs kernels
 constexpr int kMaxQpt = 2;         // query rows per thread: 2 (512-row tiles) for large sets, 1 (256-row tiles)
                                    // when the set is too small to fill the 148 SMs with 512-row tiles

@@ -22,7 +22,7 @@ namespace eb2 {
 // candidate chunk staging: D coordinate rows of one chunk -> shared memory by TMA bulk copies
 // ----------------------------------------------------------------------------------------------
 struct RowSel {
-  int row[kMaxDim];
+  int row[kMaxDimAny];
 };
 
 template <int D, int TC>
@@ -1101,5 +1101,43 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
     }
   }
 }
+
+// ----------------------------------------------------------------------------------------------
+// Generic run-time-dimension fallback (d > kMaxDim, up to kMaxDimAny): brute force, one query per
+// thread with its coordinates in local memory, candidates staged 32 at a time in shared memory,
+// k-th distance through the global-memory heap.  Same exact tests; only used for spaces wider than
+// the specialised kernels cover (rare: the estimators degrade long before).
+// ----------------------------------------------------------------------------------------------
+constexpr int kGenChunk = 32;
+
+struct GenKnnArgs {
+  const double* P;
+  int64_t stride;
+  RowSel rows;
+  int d;
+  const Tile* tiles;     // 256-row tiles
+  int ntiles;
+  int k;
+  double* eps;
+  double* heap;          // [k+1][gridDim.x * kThreads]
+  unsigned long long* pairs;
+};
+
+struct GenCountArgs {
+  const double* Q;
+  int64_t qstride;
+  const double* B;
+  int64_t bstride;
+  RowSel q_srow, b_srow;   // C shared rows
+  RowSel q_erow, b_erow;   // E extra rows
+  int C, E;
+  const double* radius;
+  const Tile* tiles;
+  int ntiles;
+  int* cnt_s;
+  int* cnt_e0;
+  int* cnt_e1;
+  unsigned long long* pairs;
+};
 
 }  // namespace eb2

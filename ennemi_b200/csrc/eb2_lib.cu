@@ -240,7 +240,7 @@ PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, i
 
 PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const int* cls,
                          const std::vector<int>& class_size, int sort_row, int cell_dim = 0, int cell_row2 = -1) {
-  const double* rows[kMaxDim + 1];
+  const double* rows[kMaxDimAny + 1];
   for (int t = 0; t < d; ++t) rows[t] = raw + static_cast<int64_t>(t) * n;
   return build_point_set_rows(s, rows, d, n, cls, class_size, sort_row, cell_dim, cell_row2, nullptr);
 }
@@ -256,6 +256,7 @@ PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, i
   // 512-row tiles only when they still give every SM several CTAs; smaller sets use 256-row tiles
   ps.qpt = (n / tile_rows(kMaxQpt) >= 4 * static_cast<int64_t>(s.c.sm_count)) ? kMaxQpt : 1;
   if (const char* e = getenv("EB2_QPT")) ps.qpt = atoi(e) == 1 ? 1 : 2;   // tuning knob
+  if (d > kMaxDim) ps.qpt = 1;      // the generic wide-space kernels use 256-row tiles
   const int nseg = cls ? static_cast<int>(class_size.size()) : 1;
   std::vector<int> seg_rank(nseg);
   ps.seg_slot.resize(nseg);
@@ -338,7 +339,7 @@ PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, i
   gather_kernel<<<blocks_n, 256, 0, st>>>(ga);
   s.launches++;
   CU(cudaGetLastError());
-  if (cell_dim >= 2 && cell_row2 >= 0 && sort_row >= 0 && !cls && !getenv("EB2_NO_CELLS")) {
+  if (cell_dim >= 2 && cell_dim <= kMaxDim && cell_row2 >= 0 && sort_row >= 0 && !cls && !getenv("EB2_NO_CELLS")) {
     const int tc = chunk_len(cell_dim);
     const int nchunks = cdiv(n, tc);
     ps.cell_dim = cell_dim;
@@ -410,6 +411,17 @@ RowSel rows_range(int first, int count) {
 void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, const TileSet& ts, double* eps,
              unsigned long long* pairs) {
   if (!ts.count) return;
+  if (D > kMaxDim) {          // wider than the specialised kernels: generic brute force
+    GenKnnArgs g;
+    g.P = ps.P; g.stride = ps.stride; g.rows = rows; g.d = D; g.tiles = ts.dev; g.ntiles = ts.count; g.k = k;
+    g.eps = eps; g.pairs = pairs;
+    const int grid = std::min(ts.count, s.c.sm_count * 4);
+    g.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * kThreads);
+    knn_generic_kernel<<<grid, kThreads, 0, s.c.stream>>>(g);
+    CU(cudaGetLastError());
+    s.launches++;
+    return;
+  }
   KnnArgs a;
   a.P = ps.P; a.stride = ps.stride; a.rows = rows; a.tiles = ts.dev; a.k = k;
   a.sort_row = -1;
@@ -461,6 +473,17 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
                const RowSel& b_srow, const RowSel& q_erow, const RowSel& b_erow, const double* radius,
                const TileSet& ts, bool prune, const CountOut& out, unsigned long long* pairs) {
   if (!ts.count) return;
+  if (C + E > kMaxDim) {      // generic brute force for wide marginals
+    GenCountArgs g;
+    g.Q = qs.P; g.qstride = qs.stride; g.B = bs.P; g.bstride = bs.stride;
+    g.q_srow = q_srow; g.b_srow = b_srow; g.q_erow = q_erow; g.b_erow = b_erow; g.C = C; g.E = E;
+    g.radius = radius; g.tiles = ts.dev; g.ntiles = ts.count;
+    g.cnt_s = out.s; g.cnt_e0 = out.e0; g.cnt_e1 = out.e1; g.pairs = pairs;
+    count_generic_kernel<<<std::min(ts.count, s.c.sm_count * 8), kThreads, 0, s.c.stream>>>(g);
+    CU(cudaGetLastError());
+    s.launches++;
+    return;
+  }
   CountArgs a;
   a.Q = qs.P; a.qstride = qs.stride; a.B = bs.P; a.bstride = bs.stride;
   a.q_srow = q_srow; a.b_srow = b_srow; a.q_erow = q_erow; a.b_erow = b_erow;

@@ -48,7 +48,7 @@ extern "C" {
 #define EB2_ERR_NONFINITE 3   /* non-finite coordinate: mirrors cKDTree's ValueError */
 #define EB2_ERR_UNSUPPORTED 4 /* dimension above EB2_MAX_DIM */
 
-#define EB2_MAX_DIM 12
+#define EB2_MAX_DIM 32           /* up to 12 dimensions: specialised kernels; 13..32: generic brute-force kernels */
 
 /* flags */
 #define EB2_FLAG_DEVICE_INPUT 1u /* coords / cls are device pointers on `dev` */

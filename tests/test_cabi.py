@@ -56,8 +56,8 @@ def test_argument_errors_do_not_need_a_device():
     val = ctypes.c_double()
     assert lib.eb2_ksg_mi(0, None, 10, 3, 0, ctypes.byref(val), None, None, None) == _native.ERR_ARG
     assert b"NULL" in lib.eb2_last_error()
-    z = np.zeros((20, 8))
-    assert lib.eb2_entropy(0, z.ctypes.data, 8, 20, 3, 0, ctypes.byref(val), None) == _native.ERR_UNSUPPORTED
+    z = np.zeros((40, 8))        # 40 dimensions > EB2_MAX_DIM (32)
+    assert lib.eb2_entropy(0, z.ctypes.data, 8, 40, 3, 0, ctypes.byref(val), None) == _native.ERR_UNSUPPORTED
     part = np.zeros(8)
     part[_native.P_SUM] = 10.0
     v = _native.ksg_mi_finish(part, 5, 1)     # psi(5) + psi(1) - 10/5, host-only arithmetic

@@ -160,7 +160,7 @@ def test_edge_cases():
     with pytest.raises(ValueError, match="data must be finite"):
         nat.ksg_mi(nat.pack_coords([np.array([0.0, np.inf, 1.0, 2.0, 3.0]), np.arange(5.0)]), 2)
     with pytest.raises(NotImplementedError):
-        nat.entropy(np.zeros((13, 50)), 3)
+        nat.entropy(np.zeros((33, 50)), 3)
     big = np.random.default_rng(1).normal(size=(600, 12))
     assert np.array_equal(nat.entropy(nat.pack_coords([big]), 3, details=True)[1]["dist"], oracle.kth_distance(big, 3, backend="c"))
 
@@ -291,3 +291,36 @@ def test_ragged_classes():
             wc = oracle.conditional_semidiscrete_mi(x, y, z, k, backend="c")
         vc, pc = nat.ross_cmi(nat.pack_coords([x, z]), cls, ncls, k, details=True)
         assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"])
+
+
+@pytest.mark.parametrize("d,n,k", [(13, 3_000, 3), (20, 2_500, 5), (32, 1_111, 12)])
+def test_wide_spaces_generic_kernels(d, n, k):
+    """Joint spaces wider than the 12 dimensions the specialised kernels cover go through the generic
+    run-time-dimension kernels: entropy in d dimensions, CMI with a (d-2)-dimensional condition and
+    conditional Ross with a (d-1)-dimensional condition, all against the C oracle."""
+    import oracle
+    rng = np.random.default_rng(100 * d + k)
+    mix = rng.normal(size=(d, d)) / np.sqrt(d) + np.eye(d)
+    x = rng.normal(size=(n, d)) @ mix
+    want = oracle.knn_entropy(x, k, backend="c")
+    value, parts = nat.entropy(nat.pack_coords([x]), k, details=True)
+    assert np.array_equal(parts["dist"], want["dist"]) and close(value, want["value"])
+
+    z = x[:, 2:]
+    a = rng.normal(size=n) + z[:, 0]
+    b = rng.normal(size=n) + 0.7 * a - z[:, 1]
+    want = oracle.conditional_mi(a, b, z, k, backend="c")
+    for flags in (0, nat.FLAG_NO_PRUNE):
+        value, parts = run_gpu("cmi", {"x": a, "y": b, "z": z, "k": k}, flags)
+        for key, arr in parts.items():
+            assert np.array_equal(arr, want[key]), (d, key, flags)
+        assert close(value, want["value"])
+
+    yd = rng.integers(0, 3, n)
+    z1 = x[:, 1:]
+    a = rng.normal(size=n) + yd + z1[:, 0]
+    want = oracle.conditional_semidiscrete_mi(a, yd, z1, k, backend="c")
+    value, parts = run_gpu("cross", {"x": a, "y": yd, "z": z1, "k": k}, 0)
+    for key, arr in parts.items():
+        assert np.array_equal(arr, want[key]), (d, key)
+    assert close(value, want["value"])
