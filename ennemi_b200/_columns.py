@@ -121,6 +121,10 @@ class ColumnStore:
             have = self._on_device.get(_devices.ordinal(dev), set())
             return any(k not in have for k in keys)
 
+    def has_stats(self, tag: tuple) -> bool:
+        with self._lock:
+            return tag in self._stats
+
     def stats(self, tag: tuple, compute):
         with self._lock:
             hit = self._stats.get(tag)
@@ -169,9 +173,11 @@ class ColsTask:
         self.n_total = len(yview)
         self.single_use = False      # set by the API when the call consists of this one task
 
-    def describe(self, dev: int):
+    def describe(self, dev: int, in_call_stats: bool = False):
         """(descriptors, n) of this task for device ``dev``: uploads what is missing, computes (cached)
-        window statistics, raises the reference's errors for impossible windows."""
+        window statistics, raises the reference's errors for impossible windows.  ``in_call_stats``: leave
+        the x / y window statistics to the library call itself (``FLAG_DEVICE_STATS``; descriptors carry
+        mean = NaN) instead of asking for them first."""
         lo_pad, hi_pad = max(self.hi, 0), min(self.lo, 0)            # as _align.lagged_windows
         n_tot = self.n_total
         xs = self.xview[lo_pad - self.lag: n_tot - self.lag + hi_pad]   # views: non-integer lags raise here
@@ -191,6 +197,10 @@ class ColsTask:
             nonlocal shapes
             self.store.ensure(dev, key)
             mean, std, nkey = 0.0, 0.0, 0
+            if self.preprocess and in_call_stats and not self.store.has_stats(tag):
+                values = stream.normal((n,))
+                shapes = shapes + ((n,),)
+                return _native.ColDesc(key, off, 1, float("nan"), 1.0, NoiseBank.key_for(shapes, values, dev), 0, 1)
             if self.preprocess:
                 mean, std = self.store.stats(tag, stats_of(key, off, view))
                 if abs(std) < _align.CONSTANT_STD:
@@ -205,13 +215,14 @@ class ColsTask:
             return _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
 
         device_stats = n >= DEVICE_STATS_MIN_ROWS
+        in_call_stats = in_call_stats and device_stats
 
         def stats_of(key, off, view):
             if device_stats:      # NumPy-exact pairwise mean/std where the column already is (eb2_cache_stats)
                 return lambda: _native.cache_stats(key, off, n, dev=dev)
             return lambda: window_stats(view)
 
-        if n >= OVERLAP_MIN_ROWS and self.preprocess and self.store.missing(dev, self.xkey, self.ykey):
+        if n >= OVERLAP_MIN_ROWS and self.preprocess and not in_call_stats and self.store.missing(dev, self.xkey, self.ykey):
             # large first-time windows: the two uploads (and statistics) run side by side on two stream lanes
             def side(key, off, view, lane_dev):
                 self.store.ensure(lane_dev, key)
@@ -251,7 +262,18 @@ class ColsTask:
 
     def run(self) -> float:
         dev = _devices.current()
-        descs, n = self.describe(dev)
+        from . import distributed
+        sharded = distributed.row_sharding_enabled()
+        # a one-task call on a large window: upload, statistics, rescaling and the estimate in ONE library call
+        descs, n = self.describe(dev, self.single_use and self.preprocess and not sharded)
+        if any(d.mean != d.mean for d in descs):
+            try:
+                return self._estimate(dev, descs, n, _native.FLAG_SINGLE_USE | _native.FLAG_DEVICE_STATS)
+            except _native.ConstantWindow:       # rare: the reference's constant-data warning path needs the value of std
+                descs, n = self.describe(dev, False)
+        return self._estimate(dev, descs, n, _native.FLAG_SINGLE_USE if self.single_use else 0)
+
+    def _estimate(self, dev: int, descs, n: int, flags: int) -> float:
         try:
             from . import distributed
             if distributed.row_sharding_enabled():
@@ -262,7 +284,6 @@ class ColsTask:
                 if self.zkeys:
                     return _native.cmi_finish(part, n, self.k)
                 return _native.ksg_mi_finish(part, n, self.k)
-            flags = _native.FLAG_SINGLE_USE if self.single_use else 0
             if self.zkeys:
                 return _native.cmi_cols(descs, n, self.k, dev=dev, flags=flags)
             return _native.ksg_mi_cols(descs, n, self.k, dev=dev, flags=flags)

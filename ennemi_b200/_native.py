@@ -19,8 +19,9 @@ FLAG_DEVICE_INPUT = 1
 FLAG_BRUTE_COUNT = 2
 FLAG_NO_PRUNE = 4
 FLAG_SINGLE_USE = 8
+FLAG_DEVICE_STATS = 16
 
-ERR_CUDA, ERR_ARG, ERR_NONFINITE, ERR_UNSUPPORTED = 1, 2, 3, 4
+ERR_CUDA, ERR_ARG, ERR_NONFINITE, ERR_UNSUPPORTED, ERR_CONSTANT = 1, 2, 3, 4, 5
 P_LEN = 8
 P_SUM, P_ZERO_A, P_ZERO_B, P_ZERO_C, P_ROWS, P_PAIRS = 0, 1, 2, 3, 4, 5
 
@@ -330,6 +331,10 @@ class NonFiniteInput(ValueError):
         self.nan = nan
 
 
+class ConstantWindow(Exception):
+    """``FLAG_DEVICE_STATS``: a window was constant; the task has to be repeated with host-checked statistics."""
+
+
 def cache_put(key: int, column: np.ndarray, dev: int = 0) -> None:
     lib = load()
     column = np.ascontiguousarray(column, dtype=np.float64)
@@ -352,6 +357,8 @@ def _cols_call(fn, cols, *args):
     if rc == ERR_NONFINITE:
         lib = load()
         raise NonFiniteInput(lib.eb2_last_error().decode(), bool(lib.eb2_last_data_flags() & 1))
+    if rc == ERR_CONSTANT:
+        raise ConstantWindow()
     if rc:
         _raise(rc)
     return value.value
@@ -393,6 +400,8 @@ def mi_cols_rows(cols, n: int, k: int, row_lo: int, row_hi: int, dev: int = 0, f
         rc = lib.eb2_cmi_cols_rows(dev, arr, n, len(cols) - 2, k, flags, row_lo, row_hi, partial.ctypes.data_as(_c_dp))
     if rc == ERR_NONFINITE:
         raise NonFiniteInput(lib.eb2_last_error().decode(), bool(lib.eb2_last_data_flags() & 1))
+    if rc == ERR_CONSTANT:
+        raise ConstantWindow()
     if rc:
         _raise(rc)
     return partial

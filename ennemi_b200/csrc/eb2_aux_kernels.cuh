@@ -209,13 +209,14 @@ struct PrepCol {
   double mean, std;        // std == 0: pass the values through unchanged (no rescaling, no noise)
   const double* noise;     // NULL: no noise
   long long noff, nstride;
+  const double* dstats;    // non-NULL (EB2_FLAG_DEVICE_STATS): mean = dstats[1], std = dstats[3], computed in this call
 };
 struct PrepArgs {
   PrepCol col[kMaxDimAny];
   int d;
   long long n;
   double* raw;
-  int* flags;              // bit0: NaN among the input values
+  int* flags;              // bit0: NaN among the input values, bit3: a window with device statistics is constant
 };
 
 __global__ void prep_kernel(const PrepArgs a) {
@@ -226,8 +227,17 @@ __global__ void prep_kernel(const PrepArgs a) {
   const PrepCol& c = a.col[t];
   double v = c.src[c.off + i * c.stride];
   if (v != v) atomicOr(a.flags, 1);
-  if (c.std != 0.0) {
-    v = __ddiv_rn(__dsub_rn(v, c.mean), c.std);
+  double mean = c.mean, std = c.std;
+  if (c.dstats && std != 0.0) {
+    mean = c.dstats[1];
+    std = c.dstats[3];
+    if (fabs(std) < 1e-20) {       // ennemi/_driver.py:879: the caller has to take the warning path
+      if (i == 0) atomicOr(a.flags, 8);
+      std = 0.0;
+    }
+  }
+  if (std != 0.0) {
+    v = __ddiv_rn(__dsub_rn(v, mean), std);
     if (c.noise) v = __dadd_rn(v, c.noise[c.noff + i * c.nstride]);
   }
   a.raw[idx] = v;
@@ -239,20 +249,34 @@ __global__ void prep_kernel(const PrepArgs a) {
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail; larger ranges split at n/2 rounded down to a
 // multiple of 8, recursively.  Reproducing that association exactly gives the same bits as ndarray.mean()
 // / ndarray.std() (tests/test_gpu_api.py checks it), so the statistics the rescaling uses can be computed
-// where the data already is.  The host supplies the leaf table of the recursion for this n.
+// where the data already is.  The host supplies the leaf table and the tree of the recursion for this n.
 struct NpLeaf {
   long long off;   // first element of the leaf (window-relative)
   int len;         // <= 128
 };
 
-// one thread per leaf; mode 0: sum of x, mode 1: sum of (x - mean)^2 with mean read from *mean_ptr
-__global__ void np_leaf_sum_kernel(const double* src, long long off, long long stride, const NpLeaf* leaves, int nleaves,
-                                   int mode, const double* mean_ptr, double* leaf_sum) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nleaves) return;
-  const NpLeaf lf = leaves[t];
-  const double mean = mode ? *mean_ptr : 0.0;
-  const double* p = src + off + lf.off * stride;
+// Statistics of up to kNpCols windows of one length per launch (blockIdx.y = window).
+constexpr int kNpCols = 8;
+struct NpCols {
+  const double* src[kNpCols];
+  long long off[kNpCols], stride[kNpCols];
+  double* out[kNpCols];      // 4 doubles per window: sum, mean, sum of squared deviations, std
+  double* val[kNpCols];      // nleaves + ninner node values of the summation tree
+};
+
+// mode 0: leaf sums of x, mode 1: of (x - mean)^2 with the mean read from out[1].
+// Eight lanes per leaf: lane j owns NumPy's accumulator r_j, so a leaf's 64-byte groups are read coalesced
+// and the shuffle tree below is exactly ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)).
+__global__ void np_leaf_sum_kernel(const NpCols a, const NpLeaf* leaves, int nleaves, int mode) {
+  const int w = blockIdx.y;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = g >> 3, j = g & 7;
+  const bool live = t < nleaves;
+  NpLeaf lf{0, 0};
+  if (live) lf = leaves[t];
+  const double mean = mode ? a.out[w][1] : 0.0;
+  const long long stride = a.stride[w];
+  const double* p = a.src[w] + a.off[w] + lf.off * stride;
   auto at = [&](int i) {
     const double v = p[(long long)i * stride];
     if (mode == 0) return v;
@@ -260,61 +284,48 @@ __global__ void np_leaf_sum_kernel(const double* src, long long off, long long s
     return __dmul_rn(c, c);
   };
   const int n = lf.len;
-  double res;
-  if (n < 8) {
-    res = 0.0;
-    for (int i = 0; i < n; ++i) res = __dadd_rn(res, at(i));
-  } else {
-    double r0 = at(0), r1 = at(1), r2 = at(2), r3 = at(3), r4 = at(4), r5 = at(5), r6 = at(6), r7 = at(7);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
-      r0 = __dadd_rn(r0, at(i)); r1 = __dadd_rn(r1, at(i + 1)); r2 = __dadd_rn(r2, at(i + 2)); r3 = __dadd_rn(r3, at(i + 3));
-      r4 = __dadd_rn(r4, at(i + 4)); r5 = __dadd_rn(r5, at(i + 5)); r6 = __dadd_rn(r6, at(i + 6)); r7 = __dadd_rn(r7, at(i + 7));
-    }
-    res = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
-    for (; i < n; ++i) res = __dadd_rn(res, at(i));
+  const int body = n - (n % 8);
+  double r = 0.0;
+  if (n >= 8) {
+    r = at(j);
+    for (int i = 8; i < body; i += 8) r = __dadd_rn(r, at(i + j));
   }
-  leaf_sum[t] = res;
+  // every lane of the warp takes part in the shuffles (leaves of different lengths share a warp)
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));     // r0+r1, r2+r3, r4+r5, r6+r7
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));     // lane 0 of the group: NumPy's association
+  double res = 0.0;
+  if (j == 0) {
+    if (n >= 8) res = r;
+    for (int i = (n >= 8 ? body : 0); i < n; ++i) res = __dadd_rn(res, at(i));
+  }
+  if (live && j == 0) a.val[w][t] = res;
 }
 
-// the recursion above the leaves; `next` walks the leaf sums in order
-__device__ double np_combine(const double* leaf_sum, int& next, long long n) {
-  if (n <= 128) return leaf_sum[next++];
-  long long n2 = n / 2;
-  n2 -= n2 % 8;
-  const double a = np_combine(leaf_sum, next, n2);
-  const double b = np_combine(leaf_sum, next, n - n2);
-  return __dadd_rn(a, b);
-}
-
-// sub-trees (first leaf, element count) are summed by one thread each, then thread 0 walks the top of the tree
-struct NpSub {
-  int first_leaf;
-  long long n;
+// The recursion above the leaves, bottom-up: inner node i (value slot nleaves + i) adds its two children;
+// nodes are ordered by height and level_start[h] .. level_start[h+1] are the nodes of height h+1, which only
+// depend on lower ones.  One CTA per window, a barrier per height (~log2(n/128) + 1 of them).
+constexpr int kNpMaxLevels = 40;
+struct NpLevels {
+  int start[kNpMaxLevels + 1];
+  int nlevels;
 };
-__device__ double np_combine_top(const double* sub_sum, int& next, long long n, int depth, int top_depth) {
-  if (depth == top_depth || n <= 128) return sub_sum[next++];
-  long long n2 = n / 2;
-  n2 -= n2 % 8;
-  const double a = np_combine_top(sub_sum, next, n2, depth + 1, top_depth);
-  const double b = np_combine_top(sub_sum, next, n - n2, depth + 1, top_depth);
-  return __dadd_rn(a, b);
-}
-// out[0] = total; finish: 0 -> out[1] = total / n (the mean); 1 -> out[1] = sqrt(total / n) (the std)
-__global__ void np_combine_kernel(const double* leaf_sum, const NpSub* subs, int nsubs, long long n, int top_depth,
-                                  int finish, double* out) {
-  __shared__ double sub_sum[256];
-  const int t = threadIdx.x;
-  if (t < nsubs) {
-    int next = subs[t].first_leaf;
-    sub_sum[t] = np_combine(leaf_sum, next, subs[t].n);
+// finish: 0 -> out[0] = total, out[1] = total / n (the mean); 1 -> out[2] = total, out[3] = sqrt(total / n) (the std)
+__global__ void np_tree_kernel(const NpCols a, const int2* children, const NpLevels lv, int nleaves, long long n, int finish) {
+  double* val = a.val[blockIdx.x];
+  for (int h = 0; h < lv.nlevels; ++h) {
+    for (int i = lv.start[h] + threadIdx.x; i < lv.start[h + 1]; i += blockDim.x) {
+      const int2 c = children[i];
+      val[nleaves + i] = __dadd_rn(val[c.x], val[c.y]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (t == 0) {
-    int next = 0;
-    const double total = np_combine_top(sub_sum, next, n, 0, top_depth);
-    out[0] = total;
+  if (threadIdx.x == 0) {
+    const int ninner = lv.start[lv.nlevels];
+    const double total = val[nleaves + ninner - 1];        // the root is the last node (or the only leaf)
     const double q = __ddiv_rn(total, (double)n);
+    double* out = a.out[blockIdx.x] + 2 * finish;
+    out[0] = total;
     out[1] = finish ? __dsqrt_rn(q) : q;
   }
 }

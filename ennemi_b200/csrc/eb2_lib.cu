@@ -101,6 +101,9 @@ struct Ctx {
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
   DevShared* shared = nullptr;
+  // NumPy pairwise-summation tables of the most recent window lengths (device copies; allocated and used on `stream`)
+  struct NpTables { int64_t n; void* leaves; void* children; int nleaves, ninner; NpLevels levels; };
+  std::vector<NpTables> np_tables;
 };
 
 Ctx g_ctx[kMaxDev * kMaxLanes];
@@ -552,6 +555,95 @@ double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* c
   return out4;
 }
 
+// Leaves and inner nodes of NumPy's pairwise summation for a range of n elements.  Returns the node id of
+// the range: leaves are >= 0 (index into `leaves`), inner nodes are -(index + 1) into `inner`.
+struct NpNode { int left, right, height; };
+static int np_plan(long long n, long long off, std::vector<NpLeaf>& leaves, std::vector<NpNode>& inner) {
+  if (n <= 128) {
+    leaves.push_back(NpLeaf{off, static_cast<int>(n)});
+    return static_cast<int>(leaves.size()) - 1;
+  }
+  long long n2 = n / 2;
+  n2 -= n2 % 8;
+  const int l = np_plan(n2, off, leaves, inner);
+  const int r = np_plan(n - n2, off + n2, leaves, inner);
+  const int hl = l >= 0 ? 0 : inner[-l - 1].height, hr = r >= 0 ? 0 : inner[-r - 1].height;
+  inner.push_back(NpNode{l, r, 1 + std::max(hl, hr)});
+  return -static_cast<int>(inner.size());
+}
+
+struct StatsWindow {
+  const double* src;
+  int64_t off, stride;
+  double* out4;          // device: sum, mean, sum of squared deviations, std
+};
+
+// mean (out4[1]) and standard deviation (out4[3]) of src[off + i*stride], i < n, for every window, with NumPy's
+// association, left on the device; four small kernels per group of kNpCols windows on the lane's stream
+void device_stats(Scratch& s, const StatsWindow* win, int nwin, int64_t n) {
+  Ctx& c = s.c;
+  const Ctx::NpTables* tb = nullptr;
+  for (const auto& e : c.np_tables)
+    if (e.n == n) tb = &e;
+  if (!tb) {
+    std::vector<NpLeaf> leaves;
+    std::vector<NpNode> inner;
+    leaves.reserve(static_cast<size_t>(n / 64 + 2));
+    inner.reserve(static_cast<size_t>(n / 64 + 2));
+    np_plan(n, 0, leaves, inner);
+    const int nleaves = static_cast<int>(leaves.size()), ninner = static_cast<int>(inner.size());
+    // inner nodes by height (counting sort; the post-order root is the highest and stays last)
+    Ctx::NpTables e{};
+    e.n = n; e.nleaves = nleaves; e.ninner = ninner;
+    int maxh = 0;
+    for (const auto& nd : inner) maxh = std::max(maxh, nd.height);
+    if (maxh > kNpMaxLevels) throw CudaFail{cudaErrorInvalidValue, "summation tree too deep", __LINE__};
+    e.levels.nlevels = maxh;
+    std::vector<int> first(maxh + 2, 0);                      // first[h] = first slot of the nodes of height h
+    for (const auto& nd : inner) first[nd.height + 1]++;
+    for (int h = 1; h <= maxh + 1; ++h) first[h] += first[h - 1];
+    for (int h = 1; h <= maxh; ++h) e.levels.start[h - 1] = first[h];
+    e.levels.start[maxh] = ninner;
+    std::vector<int> slot(ninner);
+    std::vector<int> next(first);
+    for (int i = 0; i < ninner; ++i) slot[i] = next[inner[i].height]++;
+    int2* hc = s.host<int2>(std::max(ninner, 1));
+    auto id = [&](int v) { return v >= 0 ? v : nleaves + slot[-v - 1]; };
+    for (int i = 0; i < ninner; ++i) hc[slot[i]] = make_int2(id(inner[i].left), id(inner[i].right));
+    NpLeaf* hl = s.host<NpLeaf>(leaves.size());
+    std::memcpy(hl, leaves.data(), sizeof(NpLeaf) * leaves.size());
+    if (c.np_tables.size() >= 4) {
+      cudaFreeAsync(c.np_tables.front().leaves, c.stream);
+      cudaFreeAsync(c.np_tables.front().children, c.stream);
+      c.np_tables.erase(c.np_tables.begin());
+    }
+    CU(cudaMallocAsync(&e.leaves, sizeof(NpLeaf) * leaves.size(), c.stream));
+    CU(cudaMallocAsync(&e.children, sizeof(int2) * std::max(ninner, 1), c.stream));
+    CU(cudaMemcpyAsync(e.leaves, hl, sizeof(NpLeaf) * leaves.size(), cudaMemcpyHostToDevice, c.stream));
+    CU(cudaMemcpyAsync(e.children, hc, sizeof(int2) * std::max(ninner, 1), cudaMemcpyHostToDevice, c.stream));
+    c.np_tables.push_back(e);
+    tb = &c.np_tables.back();
+  }
+  const NpLeaf* dl = static_cast<const NpLeaf*>(tb->leaves);
+  const int2* dc = static_cast<const int2*>(tb->children);
+  const int blocks = cdiv(static_cast<int64_t>(tb->nleaves) * 8, 256);
+  for (int w0 = 0; w0 < nwin; w0 += kNpCols) {
+    const int m = std::min(kNpCols, nwin - w0);
+    NpCols a{};
+    for (int w = 0; w < m; ++w) {
+      a.src[w] = win[w0 + w].src; a.off[w] = win[w0 + w].off; a.stride[w] = win[w0 + w].stride;
+      a.out[w] = win[w0 + w].out4;
+      a.val[w] = s.dev<double>(static_cast<size_t>(tb->nleaves) + tb->ninner);
+    }
+    for (int mode = 0; mode < 2; ++mode) {
+      np_leaf_sum_kernel<<<dim3(blocks, m), 256, 0, c.stream>>>(a, dl, tb->nleaves, mode);
+      np_tree_kernel<<<m, 1024, 0, c.stream>>>(a, dc, tb->levels, tb->nleaves, n, mode);
+    }
+    CU(cudaGetLastError());
+    s.launches += 4;
+  }
+}
+
 // ---- input staging -------------------------------------------------------------------------------
 // The d x n block the estimators work on comes from (a) a host block (one H2D copy), (b) a device
 // block (EB2_FLAG_DEVICE_INPUT), or (c) cached device columns, sliced / strided / rescaled by
@@ -570,6 +662,7 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
     pa.d = d; pa.n = n; pa.flags = nonfinite_flag;
     std::lock_guard<std::mutex> cache_guard(s.c.shared->mu);
     auto& cache = s.c.shared->cache;
+    std::vector<StatsWindow> windows;
     for (int t = 0; t < d; ++t) {
       const eb2_col_t& c = in.cols[t];
       auto it = cache.find(c.key);
@@ -579,7 +672,7 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
         throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
       PrepCol& pc = pa.col[t];
       pc.src = it->second.first; pc.off = c.off; pc.stride = c.stride; pc.mean = c.mean; pc.std = c.std;
-      pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride;
+      pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride; pc.dstats = nullptr;
       if (c.nkey != 0) {
         auto nt = cache.find(c.nkey);
         if (nt == cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
@@ -588,7 +681,14 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
           throw CudaFail{cudaErrorInvalidValue, "noise slice outside the cached vector", __LINE__};
         pc.noise = nt->second.first;
       }
+      if ((in.flags & EB2_FLAG_DEVICE_STATS) && c.std != 0.0 && c.mean != c.mean) {
+        // statistics of the window computed here, where the column is: no host round trip before the task
+        double* st4 = s.dev<double>(4);
+        windows.push_back(StatsWindow{pc.src, c.off, c.stride, st4});
+        pc.dstats = st4;
+      }
     }
+    if (!windows.empty()) device_stats(s, windows.data(), static_cast<int>(windows.size()), n);
     double* dv = s.dev<double>(static_cast<size_t>(total));
     pa.raw = dv;
     prep_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(pa);
@@ -631,7 +731,7 @@ Derived* get_derived(Scratch& s, const eb2_col_t& col, int64_t n) {
     pa.d = 1; pa.n = n;
     PrepCol& pc = pa.col[0];
     pc.src = src->second.first; pc.off = col.off; pc.stride = col.stride; pc.mean = col.mean; pc.std = col.std;
-    pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride;
+    pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride; pc.dstats = nullptr;
     if (col.nkey != 0) {
       auto nt = sh.cache.find(col.nkey);
       if (nt == sh.cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
@@ -730,6 +830,11 @@ int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs,
   CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
   CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
   c.last_launches = s.launches;
+  if (h->nonfinite & 8) {
+    g_data_flags = h->nonfinite;
+    return fail(EB2_ERR_CONSTANT, "a window with device-computed statistics is constant (std < 1e-20): "
+                                  "repeat the task with host-checked statistics");
+  }
   if (h->nonfinite) {
     g_data_flags = h->nonfinite;
     return fail(EB2_ERR_NONFINITE, "data must be finite, check for nan or inf values");
@@ -930,20 +1035,6 @@ int eb2_cache_drop(int dev, uint64_t key) {
 
 int eb2_last_data_flags(void) { return g_data_flags; }
 
-// leaf / sub-tree tables of NumPy's pairwise summation for a range of n elements
-static void np_plan(long long n, long long off, int depth, int top_depth, std::vector<NpLeaf>& leaves, std::vector<NpSub>& subs) {
-  // a sub-tree root is a node at top_depth, or a leaf that sits above it
-  if (depth == top_depth || (depth < top_depth && n <= 128)) subs.push_back(NpSub{static_cast<int>(leaves.size()), n});
-  if (n <= 128) {
-    leaves.push_back(NpLeaf{off, static_cast<int>(n)});
-    return;
-  }
-  long long n2 = n / 2;
-  n2 -= n2 % 8;
-  np_plan(n2, off, depth + 1, top_depth, leaves, subs);
-  np_plan(n - n2, off + n2, depth + 1, top_depth, leaves, subs);
-}
-
 int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t n, double* mean, double* std_out) {
   if (key == 0 || n <= 0 || stride == 0 || !mean || !std_out) return fail(EB2_ERR_ARG, "eb2_cache_stats: bad argument");
   return guarded(dev, [&](Ctx& c) {
@@ -959,34 +1050,15 @@ int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t 
         return fail(EB2_ERR_ARG, "eb2_cache_stats: window outside the cached column");
       src = it->second.first;
     }
-    const int top_depth = 7;                       // <= 128 sub-trees
-    std::vector<NpLeaf> leaves;
-    std::vector<NpSub> subs;
-    leaves.reserve(static_cast<size_t>(n / 64 + 2));
-    np_plan(n, 0, 0, top_depth, leaves, subs);
-    const int nleaves = static_cast<int>(leaves.size()), nsubs = static_cast<int>(subs.size());
-    NpLeaf* hl = s.host<NpLeaf>(leaves.size());
-    NpSub* hs = s.host<NpSub>(subs.size());
-    std::memcpy(hl, leaves.data(), sizeof(NpLeaf) * leaves.size());
-    std::memcpy(hs, subs.data(), sizeof(NpSub) * subs.size());
-    NpLeaf* dl = s.dev<NpLeaf>(leaves.size());
-    NpSub* ds = s.dev<NpSub>(subs.size());
-    double* leaf_sum = s.dev<double>(leaves.size());
     double* out = s.dev<double>(4);
-    CU(cudaMemcpyAsync(dl, hl, sizeof(NpLeaf) * leaves.size(), cudaMemcpyHostToDevice, c.stream));
-    CU(cudaMemcpyAsync(ds, hs, sizeof(NpSub) * subs.size(), cudaMemcpyHostToDevice, c.stream));
-    const int blocks = cdiv(nleaves, 128);
-    np_leaf_sum_kernel<<<blocks, 128, 0, c.stream>>>(src, off, stride, dl, nleaves, 0, nullptr, leaf_sum);
-    np_combine_kernel<<<1, 256, 0, c.stream>>>(leaf_sum, ds, nsubs, n, top_depth, 0, out);          // out[1] = mean
-    np_leaf_sum_kernel<<<blocks, 128, 0, c.stream>>>(src, off, stride, dl, nleaves, 1, out + 1, leaf_sum);
-    np_combine_kernel<<<1, 256, 0, c.stream>>>(leaf_sum, ds, nsubs, n, top_depth, 1, out + 2);      // out[3] = std
-    CU(cudaGetLastError());
+    const StatsWindow win{src, off, stride, out};
+    device_stats(s, &win, 1, n);
     double* h = s.host<double>(4);
     CU(cudaMemcpyAsync(h, out, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
     CU(cudaStreamSynchronize(c.stream));
     *mean = h[1];
     *std_out = h[3];
-    c.last_launches = 4;
+    c.last_launches = s.launches;
     return EB2_OK;
   });
 }
@@ -1020,7 +1092,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     const Derived* dx = nullptr;
     const Derived* dy = nullptr;
     PointSet ps;
-    if (in.cols && prune && !(flags & (EB2_FLAG_BRUTE_COUNT | EB2_FLAG_SINGLE_USE)) && !getenv("EB2_NO_DERIVED")) {
+    if (in.cols && prune && !(flags & (EB2_FLAG_BRUTE_COUNT | EB2_FLAG_SINGLE_USE | EB2_FLAG_DEVICE_STATS)) && !getenv("EB2_NO_DERIVED")) {
       // prepared variables (rescaled values + their ascending order) are shared by all tasks of the call
       dx = get_derived(s, in.cols[0], n);
       dy = get_derived(s, in.cols[1], n);

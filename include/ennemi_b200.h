@@ -47,6 +47,7 @@ extern "C" {
 #define EB2_ERR_ARG 2         /* bad argument (n, k, d, pointers) */
 #define EB2_ERR_NONFINITE 3   /* non-finite coordinate: mirrors cKDTree's ValueError */
 #define EB2_ERR_UNSUPPORTED 4 /* dimension above EB2_MAX_DIM */
+#define EB2_ERR_CONSTANT 5    /* EB2_FLAG_DEVICE_STATS: a window turned out constant; nothing was estimated */
 
 #define EB2_MAX_DIM 32           /* up to 12 dimensions: specialised kernels; 13..32: generic brute-force kernels */
 
@@ -54,6 +55,11 @@ extern "C" {
 #define EB2_FLAG_DEVICE_INPUT 1u /* coords / cls are device pointers on `dev` */
 #define EB2_FLAG_BRUTE_COUNT 2u  /* count 1-D marginals with the tiled all-pairs kernel instead of sort+search */
 #define EB2_FLAG_NO_PRUNE 4u     /* visit every candidate tile (pure brute force); default is exact sorted-window pruning */
+#define EB2_FLAG_DEVICE_STATS 16u /* *_cols calls (implies SINGLE_USE: no prepared variables are cached): a descriptor with
+                                    mean = NaN and std != 0 gets its window's mean and std computed on the device inside the
+                                    call (NumPy's pairwise association, as eb2_cache_stats) - no host round trip before the
+                                    task.  A window that turns out constant (std < 1e-20, ennemi/_driver.py:879) fails the
+                                    call with EB2_ERR_CONSTANT so that the caller can take the reference's warning path */
 #define EB2_FLAG_SINGLE_USE 8u   /* *_cols calls: the descriptors are used by this task only - do not cache prepared variables */
 
 /* layout of the 8-double partial block */

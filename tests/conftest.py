@@ -90,7 +90,7 @@ class OracleBackend:
         v = self.cache[(dev & 0xFF, key)][off: off + (n - 1) * stride + 1: stride]
         return float(v.mean()), float(v.std())
 
-    def _gather(self, descs, n, dev):
+    def _gather(self, descs, n, dev, flags=0):
         from ennemi_b200 import _native
         rows = []
         for d in descs:
@@ -98,8 +98,13 @@ class OracleBackend:
             v = col[d.off: d.off + (n - 1) * d.stride + 1: d.stride].copy()
             if np.isnan(v).any():
                 raise _native.NonFiniteInput("data must be finite, check for nan or inf values", True)
-            if d.std != 0.0:
-                v = (v - d.mean) / d.std
+            mean, std = d.mean, d.std
+            if (flags & _native.FLAG_DEVICE_STATS) and std != 0.0 and mean != mean:
+                mean, std = v.mean(), v.std()                 # EB2_FLAG_DEVICE_STATS: statistics inside the call
+                if abs(std) < 1e-20:
+                    raise _native.ConstantWindow()
+            if std != 0.0:
+                v = (v - mean) / std
                 if d.nkey:
                     noise = self.cache[(dev & 0xFF, d.nkey)]
                     v = v + noise[d.noff: d.noff + (n - 1) * d.nstride + 1: d.nstride]
@@ -109,7 +114,7 @@ class OracleBackend:
         return rows
 
     def ksg_mi_cols(self, descs, n, k, dev=0, flags=0):
-        x, y = self._gather(descs, n, dev)
+        x, y = self._gather(descs, n, dev, flags)
         return self.o.ksg_mi(x, y, k, backend=self.backend)["value"]
 
     def mi_cols_batch(self, tasks, n, k, dev=0, flags=0):
@@ -123,7 +128,7 @@ class OracleBackend:
         return values, status
 
     def cmi_cols(self, descs, n, k, dev=0, flags=0):
-        rows = self._gather(descs, n, dev)
+        rows = self._gather(descs, n, dev, flags)
         return self.o.conditional_mi(rows[0], rows[1], np.column_stack(rows[2:]), k, backend=self.backend)["value"]
 
 
@@ -136,6 +141,8 @@ def oracle_backend(monkeypatch):
         monkeypatch.setattr(_native, name, getattr(fake, name))
     monkeypatch.setattr(_native, "device_count", lambda: 1)
     monkeypatch.setattr(_devices, "visible", lambda: [0])
+    from ennemi_b200 import _columns
+    monkeypatch.setattr(_columns.NoiseBank, "_on_device", {})      # a fresh fake device holds no noise vectors yet
     return fake
 
 

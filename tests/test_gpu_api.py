@@ -150,3 +150,34 @@ def test_device_statistics_have_numpy_bits():
         assert nat.cache_stats(777001, 5, 100_000, stride=3) == (float(view.mean()), float(view.std()))
     finally:
         nat.cache_drop(777001)
+
+
+def test_one_call_statistics_on_gpu(monkeypatch):
+    """One-task calls on large windows: upload, NumPy-exact statistics, rescaling and the estimate in one
+    library call (EB2_FLAG_DEVICE_STATS).  Same bits as the host-prepared path; a constant window falls back
+    to the path that warns like the reference; page-locked input arrays behave like any other array."""
+    import torch
+    from ennemi_b200 import api, _align, _native as nat
+    rng = np.random.default_rng(11)
+    n = 120_000
+    x = rng.normal(-1.0, 0.3, size=n); y = np.exp(x) + rng.normal(size=n) * 0.1
+    z = rng.normal(size=(n, 2)) + x[:, None]
+    xs, ys, zs = _align.rescaled(x, y, z, False, False)
+    want = nat.ksg_mi(nat.pack_coords([xs, ys]), 3)
+    assert eb.estimate_mi(y, x)[0, 0] == want
+    assert nat.last_timing()["launches"] > 8                 # statistics kernels ran inside the estimate call
+    assert eb.estimate_mi(y, x, cond=z)[0, 0] == nat.cmi(nat.pack_coords([xs, ys, zs]), 3)
+    assert eb.estimate_mi(y[3:], x[:-3])[0, 0] == eb.estimate_mi(y, x, lag=3)[0, 0]
+    pin = torch.empty((2, n), dtype=torch.float64, pin_memory=True).numpy()
+    pin[0] = x; pin[1] = y
+    assert eb.estimate_mi(pin[1], pin[0])[0, 0] == want
+    const = np.full(n, 0.25)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        got = eb.estimate_mi(const, x)[0, 0]
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        ref = eb.estimate_mi(const, x)[0, 0]
+    assert got == ref or (np.isnan(got) and np.isnan(ref))
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+        eb.estimate_mi(np.where(np.arange(n) == 5, np.nan, y), x)

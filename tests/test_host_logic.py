@@ -251,3 +251,36 @@ def test_class_ids_match_np_unique():
         labels, inv, cnt = np.unique(y, return_inverse=True, return_counts=True)
         c, n, sz = _classes(y)
         assert n == len(labels) and np.array_equal(c, np.ravel(inv)) and np.array_equal(sz, cnt)
+
+
+def test_one_call_statistics_path(oracle_backend, golden_api, monkeypatch):
+    """A one-task call leaves the window statistics to the library call (FLAG_DEVICE_STATS, descriptors
+    with mean = NaN); a constant window comes back as ConstantWindow and is repeated on the path that
+    knows std, which warns exactly like the reference."""
+    from ennemi_b200 import api, _columns, _native
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    monkeypatch.setattr(_columns, "DEVICE_STATS_MIN_ROWS", 0)
+    g = golden_api
+    x3, y, cond = (g["inputs"][k] for k in ("x3", "y", "cond"))
+    seen = []
+    real = oracle_backend.ksg_mi_cols
+    monkeypatch.setattr(_columns._native, "ksg_mi_cols",
+                        lambda descs, n, k, dev=0, flags=0: (seen.append((flags, [d.mean for d in descs])), real(descs, n, k, dev, flags))[1])
+    one = eb.estimate_mi(y, x3[:, 0], lag=1)
+    assert seen and seen[-1][0] & _native.FLAG_DEVICE_STATS and all(m != m for m in seen[-1][1])
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    assert eq(one, eb.estimate_mi(y, x3[:, 0], lag=1))
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host = eb.estimate_mi(y, x3[:, 1], cond=cond)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    assert eq(eb.estimate_mi(y, x3[:, 1], cond=cond), host)
+    # constant x: first attempt raises ConstantWindow inside, the repeat warns and agrees with the host path
+    const = np.full(600, 2.0)
+    n_calls = len(seen)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        dev_out = eb.estimate_mi(const, x3[:, 0])
+    assert len(seen) == n_calls + 2 and not (seen[-1][0] & _native.FLAG_DEVICE_STATS)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    with pytest.warns(UserWarning, match="takes only a single value"):
+        assert eq(dev_out, eb.estimate_mi(const, x3[:, 0]))
