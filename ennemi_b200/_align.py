@@ -128,6 +128,14 @@ class _NoiseStream:
         return hit
 
 
+    def skip(self, shape) -> None:
+        """Advance past a draw whose values the caller already has."""
+        shape = tuple(shape)
+        if self._rng is not None:
+            self._rng.normal(0.0, NOISE_SCALE, shape)
+        self._shapes = self._shapes + (shape,)
+
+
 def rescaled(xs, ys, zs, discrete_x: bool, discrete_y: bool):
     """Unit variance plus N(0, 1e-10) noise from a fixed-seed generator; draw order x, y, z;
     discrete variables consume no draws; (near-)constant data is left alone with a warning

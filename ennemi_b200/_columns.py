@@ -96,25 +96,71 @@ class NoiseBank:
 
 
 class ColumnStore:
-    """The variables of one API call, uploaded lazily to each GPU that runs one of its tasks."""
+    """The variables of one API call, uploaded lazily to each GPU that runs one of its tasks.
 
-    def __init__(self):
+    Columns of a row-major 2-D array (the ``(n, nvar)`` layout ``pairwise_mi`` and multi-variable
+    ``estimate_mi`` receive) are registered as one *block*: the first task that needs any of them on a GPU
+    uploads the whole block with one copy and the device de-interleaves it (``eb2_cache_put_block``) — the
+    host never gathers strided columns."""
+
+    # a block is uploaded whole only if its columns fill at least this fraction of its rows' stride
+    MIN_BLOCK_DENSITY = 0.25
+
+    def __init__(self, full_stats: bool = False):
         self._cols: Dict[int, np.ndarray] = {}
         self._on_device: Dict[int, set] = {}
         self._lock = threading.Lock()
         self._stats: Dict[tuple, tuple] = {}
+        self._blocks: List[Tuple[np.ndarray, List[int]]] = []
+        self._block_of: Dict[int, int] = {}
+        self._descs: Dict[tuple, tuple] = {}
+        # whole-column mean/std of every block column computed right after the upload, in one call
+        # (the windows of every pairwise_mi task; lagged windows are computed on demand)
+        self.full_stats = full_stats
 
     def add(self, column: np.ndarray) -> int:
         key = _new_key()
         self._cols[key] = np.ascontiguousarray(column, dtype=np.float64)
         return key
 
+    def add_columns(self, block: np.ndarray) -> List[int]:
+        """One key per column of a 2-D array (or the single key of a 1-D one)."""
+        if block.ndim == 1:
+            return [self.add(block)]
+        ld = _native.block_layout(block)
+        if ld is None or block.shape[1] < self.MIN_BLOCK_DENSITY * ld:
+            return [self.add(block[:, j]) for j in range(block.shape[1])]
+        keys = [_new_key() for _ in range(block.shape[1])]
+        self._blocks.append((block, keys))
+        for j, key in enumerate(keys):
+            self._cols[key] = block[:, j]
+            self._block_of[key] = len(self._blocks) - 1
+        return keys
+
     def ensure(self, dev: int, key: int) -> None:
         with self._lock:
             have = self._on_device.setdefault(_devices.ordinal(dev), set())
-            if key not in have:
+            if key in have:
+                return
+            bid = self._block_of.get(key)
+            if bid is None:
                 _native.cache_put(key, self._cols[key], dev=dev)
                 have.add(key)
+                return
+            block, keys = self._blocks[bid]
+            _native.cache_put_block(keys, block, dev=dev)
+            have.update(keys)
+            n = block.shape[0]
+            if self.full_stats and n >= DEVICE_STATS_MIN_ROWS:
+                means, stds = _native.cache_stats_many(keys, [0] * len(keys), n, dev=dev)
+                for k, m, sd in zip(keys, means, stds):
+                    self._stats.setdefault((k, 0, n), (float(m), float(sd)))
+
+    def cached_desc(self, tag: tuple):
+        return self._descs.get(tag)
+
+    def remember_desc(self, tag: tuple, desc, drew: bool) -> None:
+        self._descs[tag] = (desc, drew)
 
     def missing(self, dev: int, *keys) -> bool:
         with self._lock:
@@ -143,6 +189,9 @@ class ColumnStore:
                     pass
         self._on_device.clear()
         self._cols.clear()
+        self._blocks.clear()
+        self._block_of.clear()
+        self._descs.clear()
 
 
 def eligible(arrays, mask, drop_nan: bool, discrete_any: bool) -> bool:
@@ -193,26 +242,42 @@ class ColsTask:
         stream = _align._NoiseStream()
         descs: List[_native.ColDesc] = []
 
+        ordinal = _devices.ordinal(dev)
+
         def one(key, off, view, tag):
+            # the descriptor of a variable in a given role (= position in the draw sequence) is the same for every
+            # task of the call that uses it there: pairwise_mi asks for each column 63 times
             nonlocal shapes
+            memo = (tag, shapes, ordinal, self.preprocess)
+            hit = None if in_call_stats else self.store.cached_desc(memo)
+            if hit is not None:
+                if hit[1]:
+                    stream.skip((n,))
+                    shapes = shapes + ((n,),)
+                return hit[0]
             self.store.ensure(dev, key)
             mean, std, nkey = 0.0, 0.0, 0
             if self.preprocess and in_call_stats and not self.store.has_stats(tag):
                 values = stream.normal((n,))
                 shapes = shapes + ((n,),)
                 return _native.ColDesc(key, off, 1, float("nan"), 1.0, NoiseBank.key_for(shapes, values, dev), 0, 1)
+            reusable = True
             if self.preprocess:
                 mean, std = self.store.stats(tag, stats_of(key, off, view))
                 if abs(std) < _align.CONSTANT_STD:
                     warnings.warn(_align.CONSTANT_DATA_WARNING)
                     std = 0.0
+                    reusable = False                                # every task warns, as in the reference
                 elif std == std:                                    # NaN std (NaN input): reported by the device
                     values = stream.normal((n,))
                     shapes = shapes + ((n,),)
                     nkey = NoiseBank.key_for(shapes, values, dev)
                 else:
                     std = 0.0
-            return _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
+            desc = _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
+            if reusable and not in_call_stats:
+                self.store.remember_desc(memo, desc, nkey != 0)
+            return desc
 
         device_stats = n >= DEVICE_STATS_MIN_ROWS
         in_call_stats = in_call_stats and device_stats

@@ -35,6 +35,7 @@ EXPORTS = (
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
+    "eb2_cache_put_block", "eb2_cache_stats_many",
 )
 
 _lib = None
@@ -90,6 +91,8 @@ def load():
         lib.eb2_measure_fp64_peak.argtypes = [_int, _c_dp]
         lib.eb2_cache_put.argtypes = [_int, ctypes.c_uint64, _vp, _i64]
         lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
+        lib.eb2_cache_put_block.argtypes = [_int, _vp, _int, _vp, _i64, _i64]
+        lib.eb2_cache_stats_many.argtypes = [_int, _vp, _vp, _int, _i64, _i64, _vp, _vp]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
         lib.eb2_ksg_mi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _i64, _i64, _c_dp]
@@ -341,6 +344,43 @@ def cache_put(key: int, column: np.ndarray, dev: int = 0) -> None:
     rc = lib.eb2_cache_put(dev, key, column.ctypes.data, column.size)
     if rc:
         _raise(rc)
+
+
+def block_layout(block: np.ndarray):
+    """Row stride (in elements) of a 2-D float64 array whose rows are runs of consecutive doubles — the
+    layout ``eb2_cache_put_block`` uploads with one copy — or None for any other layout."""
+    if block.ndim != 2 or block.dtype != np.float64 or block.shape[0] == 0 or block.shape[1] < 2:
+        return None
+    s0, s1 = block.strides
+    if s1 != 8 or s0 % 8 != 0 or s0 < 8 * block.shape[1]:
+        return None
+    return s0 // 8
+
+
+def cache_put_block(keys: Sequence[int], block: np.ndarray, dev: int = 0) -> None:
+    """Caches every column of a row-major ``(n, ncols)`` float64 block (see :func:`block_layout`) with one
+    host-to-device copy; the de-interleave runs on the device."""
+    lib = load()
+    ld = block_layout(block)
+    if ld is None or len(keys) != block.shape[1]:
+        raise ValueError("cache_put_block: need a 2-D float64 array with unit column stride and one key per column")
+    karr = np.asarray(keys, dtype=np.uint64)
+    rc = lib.eb2_cache_put_block(dev, karr.ctypes.data, len(keys), block.ctypes.data, block.shape[0], ld)
+    if rc:
+        _raise(rc)
+
+
+def cache_stats_many(keys: Sequence[int], offs: Sequence[int], n: int, stride: int = 1, dev: int = 0):
+    """(means, stds) arrays of several same-length cached column windows: one call, NumPy's bits."""
+    lib = load()
+    karr = np.asarray(keys, dtype=np.uint64)
+    oarr = np.asarray(offs, dtype=np.int64)
+    means, stds = np.empty(len(karr)), np.empty(len(karr))
+    rc = lib.eb2_cache_stats_many(dev, karr.ctypes.data, oarr.ctypes.data, len(karr), stride, n,
+                                  means.ctypes.data, stds.ctypes.data)
+    if rc:
+        _raise(rc)
+    return means, stds
 
 
 def cache_drop(key: int, dev: int = 0) -> None:

@@ -206,9 +206,11 @@ def estimate_mi(y, x, lag=0, *, k: int = 3, cond=None, cond_lag=0, mask=None,
     store = _device_store([x_arr, y_arr, cond_arr], mask_arr, drop_nan, discrete_x or discrete_y)
     if store is not None:
         # every variable goes to the GPU once; a task is a set of lag offsets into the cached columns
-        xkeys = [store.add(c) for c in x_cols]
+        # (a row-major (n, nvar) array travels as one block and is split into columns on the device)
+        store.full_stats = bool(preprocess and hi == 0 and lo == 0 and n_var > 1)
+        xkeys = store.add_columns(x_arr)
         ykey = store.add(y_arr)
-        zkeys = [] if cond_arr is None else [store.add(cond_arr[:, j]) for j in range(n_cond)]
+        zkeys = [] if cond_arr is None else store.add_columns(cond_arr)
         tasks = [ColsTask(store, xkeys[v], ykey, zkeys, x_cols[v], y_arr, cond_arr, lags[li], hi, lo, cond_lags[li],
                           k, preprocess) for li, v in cells]
         if len(tasks) == 1:
@@ -283,8 +285,9 @@ def pairwise_mi(data, *, k: int = 3, cond=None, mask=None, discrete=False, prepr
     pairs = [(i, j) for i in range(n_var) for j in range(i + 1, n_var)]
     store = _device_store([data_arr, cond_arr], mask_arr, drop_nan, bool(flags.any()))
     if store is not None:
-        keys = [store.add(data_arr[:, v]) for v in range(n_var)]
-        zkeys = [] if cond_arr is None else [store.add(cond_arr[:, j]) for j in range(cond_arr.shape[1])]
+        store.full_stats = bool(preprocess)
+        keys = store.add_columns(data_arr)
+        zkeys = [] if cond_arr is None else store.add_columns(cond_arr)
         tasks = [ColsTask(store, keys[i], keys[j], zkeys, data_arr[:, i], data_arr[:, j], cond_arr, 0, 0, 0,
                           np.atleast_1d(zero_lag), k, preprocess) for i, j in pairs]
     else:

@@ -1016,6 +1016,53 @@ int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
   });
 }
 
+// One H2D copy of a row-major (n x ncols) block (row stride ld >= ncols elements) and a device-side
+// de-interleave into ncols cached columns: replaces ncols strided gathers on the host (pairwise_mi on an
+// (n, nvar) array spent more time transposing on the CPU than estimating on the GPU).
+int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* host, int64_t n, int64_t ld) {
+  if (!keys || !host || ncols <= 0 || n <= 0 || ld < ncols) return fail(EB2_ERR_ARG, "eb2_cache_put_block: bad argument");
+  for (int j = 0; j < ncols; ++j)
+    if (keys[j] == 0) return fail(EB2_ERR_ARG, "eb2_cache_put_block: key 0 is reserved");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    const size_t count = static_cast<size_t>(n) * ncols;
+    double* block = s.dev<double>(count);
+    if (ld == ncols)
+      CU(cudaMemcpyAsync(block, host, sizeof(double) * count, cudaMemcpyHostToDevice, c.stream));
+    else
+      CU(cudaMemcpy2DAsync(block, sizeof(double) * ncols, host, sizeof(double) * ld, sizeof(double) * ncols,
+                           static_cast<size_t>(n), cudaMemcpyHostToDevice, c.stream));
+    std::vector<double*> cols(ncols, nullptr);
+    try {
+      for (int j = 0; j < ncols; ++j)
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&cols[j]), sizeof(double) * n, c.stream));
+      double** table_h = s.host<double*>(ncols);
+      std::memcpy(table_h, cols.data(), sizeof(double*) * ncols);
+      double** table_d = s.dev<double*>(ncols);
+      CU(cudaMemcpyAsync(table_d, table_h, sizeof(double*) * ncols, cudaMemcpyHostToDevice, c.stream));
+      deinterleave_kernel<<<dim3(cdiv(n, 32), cdiv(ncols, 32)), dim3(32, 8), 0, c.stream>>>(block, n, ncols, table_d);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(c.stream));      // the caller may reuse `host` right away
+    } catch (...) {
+      for (double* p : cols)
+        if (p) cudaFreeAsync(p, c.stream);
+      throw;
+    }
+    c.last_launches = 1;
+    std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+    for (int j = 0; j < ncols; ++j) {
+      auto it = c.shared->cache.find(keys[j]);
+      if (it != c.shared->cache.end()) {
+        cudaFreeAsync(it->second.first, c.stream);
+        c.shared->cache.erase(it);
+      }
+      c.shared->cache[keys[j]] = {cols[j], n};
+    }
+    return EB2_OK;
+  });
+}
+
 int eb2_cache_drop(int dev, uint64_t key) {
   return guarded(dev, [&](Ctx& c) {
     CU(cudaSetDevice(c.dev));
@@ -1058,6 +1105,37 @@ int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t 
     CU(cudaStreamSynchronize(c.stream));
     *mean = h[1];
     *std_out = h[3];
+    c.last_launches = s.launches;
+    return EB2_OK;
+  });
+}
+
+// eb2_cache_stats for nwin windows of one length in one call (one group of launches, one read-back)
+int eb2_cache_stats_many(int dev, const uint64_t* keys, const int64_t* offs, int nwin, int64_t stride, int64_t n,
+                         double* means, double* stds) {
+  if (!keys || !offs || nwin <= 0 || n <= 0 || stride == 0 || !means || !stds)
+    return fail(EB2_ERR_ARG, "eb2_cache_stats_many: bad argument");
+  return guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    double* out = s.dev<double>(static_cast<size_t>(nwin) * 4);
+    std::vector<StatsWindow> wins(nwin);
+    {
+      std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+      for (int w = 0; w < nwin; ++w) {
+        auto it = c.shared->cache.find(keys[w]);
+        if (it == c.shared->cache.end()) return fail(EB2_ERR_ARG, "eb2_cache_stats_many: column key not in the device cache");
+        const int64_t last = offs[w] + (n - 1) * stride;
+        if (offs[w] < 0 || last < 0 || offs[w] >= it->second.second || last >= it->second.second)
+          return fail(EB2_ERR_ARG, "eb2_cache_stats_many: window outside the cached column");
+        wins[w] = StatsWindow{it->second.first, offs[w], stride, out + 4 * w};
+      }
+    }
+    device_stats(s, wins.data(), nwin, n);
+    double* h = s.host<double>(static_cast<size_t>(nwin) * 4);
+    CU(cudaMemcpyAsync(h, out, sizeof(double) * 4 * nwin, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    for (int w = 0; w < nwin; ++w) { means[w] = h[4 * w + 1]; stds[w] = h[4 * w + 3]; }
     c.last_launches = s.launches;
     return EB2_OK;
   });

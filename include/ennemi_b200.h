@@ -144,11 +144,19 @@ EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
  * fixed-seed noise vector, bit-identically) ------------------------------------------------------- */
 EB2_API int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n);  /* key != 0; replaces */
 EB2_API int eb2_cache_drop(int dev, uint64_t key);                               /* key == 0: everything */
+/* ncols columns at once from a row-major (n x ncols) host block with row stride `ld` elements (ld >= ncols): ONE
+ * host-to-device copy, then a de-interleave kernel on the device.  Column j of the block is cached under keys[j].
+ * Replaces the per-column strided gathers the host would otherwise do for the (n, nvar) arrays the reference's
+ * pairwise_mi / estimate_mi take (ennemi/_driver.py:477-483, 703-707 slice them column by column). */
+EB2_API int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* host, int64_t n, int64_t ld);
 
 /* mean and standard deviation (ddof = 0) of the window column[key][off + i*stride], i in [0, n), computed on the
  * device with NumPy's pairwise-summation association, i.e. the same bits as ndarray.mean() / ndarray.std()
  * (the values _rescale_data uses, ennemi/_driver.py:878-882). */
 EB2_API int eb2_cache_stats(int dev, uint64_t key, int64_t off, int64_t stride, int64_t n, double* mean, double* std);
+/* ... for nwin windows of one length in one call: window w = column[keys[w]][offs[w] + i*stride] */
+EB2_API int eb2_cache_stats_many(int dev, const uint64_t* keys, const int64_t* offs, int nwin, int64_t stride, int64_t n,
+                                 double* means, double* stds);
 
 /* coordinate t of the joint space, for i in [0, n):
  *   v_i = column[key][off + i * stride]

@@ -40,7 +40,8 @@ class OracleBackend:
     signatures, answers computed by the CPU oracle.  Never used by the product."""
 
     PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
-               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch", "cache_stats")
+               "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch", "cache_stats",
+               "cache_put_block", "cache_stats_many")
 
     def __init__(self, backend="scipy"):
         import oracle
@@ -82,6 +83,17 @@ class OracleBackend:
     # ---- device column cache, emulated with numpy (same three IEEE operations as prep_kernel)
     def cache_put(self, key, column, dev=0):
         self.cache[(dev & 0xFF, key)] = np.array(column, dtype=np.float64).ravel()
+
+    def cache_put_block(self, keys, block, dev=0):
+        from ennemi_b200 import _native
+        assert _native.block_layout(block) is not None and len(keys) == block.shape[1]
+        self.block_puts = getattr(self, "block_puts", 0) + 1
+        for j, key in enumerate(keys):
+            self.cache[(dev & 0xFF, key)] = np.array(block[:, j], dtype=np.float64)
+
+    def cache_stats_many(self, keys, offs, n, stride=1, dev=0):
+        pairs = [self.cache_stats(k, o, n, stride, dev) for k, o in zip(keys, offs)]
+        return np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
 
     def cache_drop(self, key, dev=0):
         self.cache.pop((dev & 0xFF, key), None)

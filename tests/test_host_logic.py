@@ -200,7 +200,7 @@ def test_device_column_path_gives_identical_results(oracle_backend, golden_api, 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         assert eq(eb.estimate_mi(y, x3, lags), g["mi_lags"]["out"])
-        assert len(puts) >= 4                                           # the fast path really ran
+        assert len(puts) >= 3 and oracle_backend.block_puts == 1         # the fast path really ran (x3 as one block)
         assert eq(eb.estimate_mi(y, x3, lags, k=5, preprocess=False), g["mi_lags_k5_nopre"]["out"])
         assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond), g["mi_cond"]["out"])
         assert eq(eb.estimate_mi(y, x3[:, :2], lags, cond=cond, cond_lag=1), g["mi_cond_lag1"]["out"])
@@ -284,3 +284,50 @@ def test_one_call_statistics_path(oracle_backend, golden_api, monkeypatch):
     monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
     with pytest.warns(UserWarning, match="takes only a single value"):
         assert eq(dev_out, eb.estimate_mi(const, x3[:, 0]))
+
+
+def test_block_upload_path(oracle_backend, monkeypatch):
+    """Row-major (n, nvar) arrays are registered as one block per call: one upload per device instead of one
+    strided gather per column, whole-column statistics in one call, descriptors memoised per (variable, role) —
+    and results identical to the general host path, warnings included."""
+    from ennemi_b200 import api, _columns, _native
+    rng = np.random.default_rng(5)
+    data = rng.normal(size=(400, 6)) @ rng.normal(size=(6, 6))
+    cond = rng.normal(size=(400, 2)) + data[:, :2]
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host_pw = eb.pairwise_mi(data)
+    host_pw_c = eb.pairwise_mi(data, cond=cond)
+    host_mi = eb.estimate_mi(data[:, 0], data[:, 1:], lag=[0, 2, -1])
+    host_np = eb.pairwise_mi(data, preprocess=False)
+    wide = np.zeros((400, 40)); wide[:, :6] = data
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    for stats_rows in (0, 10 ** 9):                 # whole-column statistics on the "device" / lazily on the host
+        monkeypatch.setattr(_columns, "DEVICE_STATS_MIN_ROWS", stats_rows)
+        single_puts = []
+        real_put = oracle_backend.cache_put
+        monkeypatch.setattr(_columns._native, "cache_put",
+                            lambda key, col, dev=0: (single_puts.append(key), real_put(key, col, dev))[1])
+        oracle_backend.block_puts = 0
+        assert eq(eb.pairwise_mi(data), host_pw)
+        assert oracle_backend.block_puts == 1 and len(single_puts) <= 2          # only noise vectors go one by one
+        assert eq(eb.pairwise_mi(data, cond=cond), host_pw_c)
+        assert eq(eb.estimate_mi(data[:, 0], data[:, 1:], lag=[0, 2, -1]), host_mi)      # a strided block (ld = 6, 5 columns)
+        assert eq(eb.pairwise_mi(data, preprocess=False), host_np)
+        assert eq(eb.pairwise_mi(np.asfortranarray(data)), host_pw)                     # contiguous columns: no block
+        before = oracle_backend.block_puts
+        assert eq(eb.pairwise_mi(wide[:, :6]), host_pw)                                  # sparse view: column by column
+        assert oracle_backend.block_puts == before
+    # layouts
+    assert _native.block_layout(data) == 6 and _native.block_layout(data[:, 1:]) == 6
+    assert _native.block_layout(data[:, ::2]) is None and _native.block_layout(np.asfortranarray(data)) is None
+    assert _native.block_layout(data.astype(np.float32)) is None and _native.block_layout(data[:, :1]) is None
+    # a constant column warns for every task that touches it, on both paths, and is never memoised
+    const = data.copy(); const[:, 2] = 1.5
+    with warnings.catch_warnings(record=True) as w_dev:
+        warnings.simplefilter("always")
+        out_dev = eb.pairwise_mi(const)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    with warnings.catch_warnings(record=True) as w_host:
+        warnings.simplefilter("always")
+        out_host = eb.pairwise_mi(const)
+    assert eq(out_dev, out_host) and len(w_dev) == len(w_host) == 5
