@@ -70,6 +70,9 @@ struct KnnArgs {
   struct LeftEntry* left_list;
   unsigned int* left_count;
   double* left_best;     // [slot][K1T]
+  // two-level layout, register top-k variants, <= 3-D: warp windows of at most this many slots are walked per lane
+  // (each lane only ITS OWN window of the in-chunk coordinate, see knn_scan_lane); 0 = always the all-lanes scan
+  int lane_scan;
 };
 
 // sorted ascending register list; precondition v < best[K1T-1].  No NaNs can reach here (a NaN
@@ -286,6 +289,84 @@ __device__ __forceinline__ void knn_scan_chunk(const double* sbuf, int lo, int h
   }
 }
 
+// Per-lane scan of the slots [rlo, rhi) of a staged chunk, which ascend in coordinate 1 (two-level layout).
+// Each query walks only the slots that can still enter ITS list: the first slot s with fl(q1 - y_s) < thr is
+// found by binary search (the rounded subtraction is monotone in y_s, so the predicate is monotone in s) and
+// the walk stops at the first slot with fl(y_s - q1) >= thr (monotone again; thr only shrinks on the way).
+// Slots outside that run fail the coordinate-1 test of inside_lt, so skipping them cannot change any list: the
+// tests on the slots looked at are the same as in knn_scan_chunk, hence bit-exact.  Slots [skip_a, skip_b)
+// were already examined (seeding) and must not enter a list twice.
+template <int D, int K1T, int TC, bool SKIP>
+__device__ __forceinline__ void knn_scan_lane(const double* sbuf, int rlo, int rhi, const double (&q)[D], double (&best)[K1T],
+                                              double& thr, int skip_a, int skip_b, unsigned long long& npairs) {
+  // rlo is a multiple of G; slots are walked in aligned groups of G (independent loads, one branch per group:
+  // long windows in sparse regions are not one dependent chain per slot).  Slots of a group that lie before
+  // the lane's window, or in the NaN padding past the chunk's last row, simply fail the exact test.
+  constexpr int G = 4;
+  const double* sy = sbuf + TC;
+  const double q1 = q[1];
+  int lo = rlo, hi = rhi;
+  {
+    const double t0 = thr;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((q1 - sy[mid]) < t0) hi = mid; else lo = mid + 1;
+    }
+  }
+#pragma unroll 1
+  for (int s = lo & ~(G - 1); s < rhi; s += G) {
+    double c[G][D];
+    {
+      const double2 y01 = *reinterpret_cast<const double2*>(&sy[s]);
+      if (!((y01.x - q1) < thr)) break;
+      const double2 y23 = *reinterpret_cast<const double2*>(&sy[s + 2]);
+      c[0][1] = y01.x; c[1][1] = y01.y; c[2][1] = y23.x; c[3][1] = y23.y;
+    }
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+      if (t == 1) continue;
+      const double2 v01 = *reinterpret_cast<const double2*>(&sbuf[t * TC + s]);
+      const double2 v23 = *reinterpret_cast<const double2*>(&sbuf[t * TC + s + 2]);
+      c[0][t] = v01.x; c[1][t] = v01.y; c[2][t] = v23.x; c[3][t] = v23.y;
+    }
+    npairs += G;
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      bool h = inside_lt<D>(q, c[u], thr);
+      if (SKIP) h = h && (s + u < skip_a || s + u >= skip_b);
+      any = any || h;
+    }
+    if (any) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        if (SKIP && s + u >= skip_a && s + u < skip_b) continue;
+        if (inside_lt<D>(q, c[u], thr)) {
+          topk_insert<K1T>(best, cheb<D>(q, c[u]));
+          thr = best[K1T - 1];
+        }
+      }
+    }
+  }
+}
+
+// every slot of [sa, sb) against one query, no window (seeding: thr starts at +inf)
+template <int D, int K1T, int TC>
+__device__ __forceinline__ void knn_seed_lane(const double* sbuf, int sa, int sb, const double (&q)[D], double (&best)[K1T],
+                                              double& thr, unsigned long long& npairs) {
+#pragma unroll 1
+  for (int s = sa; s < sb; ++s) {
+    double c[D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) c[t] = sbuf[t * TC + s];
+    if (inside_lt<D>(q, c, thr)) {
+      topk_insert<K1T>(best, cheb<D>(q, c));
+      thr = best[K1T - 1];
+    }
+  }
+  npairs += (unsigned long long)max(0, sb - sa);
+}
+
 // K1T > 0: register-resident sorted top-K1T (k+1 <= K1T).  K1T == 0: heap in global scratch, any k.
 template <int D, int K1T, int QPT>
 __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_kernel(const KnnArgs a) {
@@ -399,6 +480,109 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
           lo = lower_bound_ge(sy, lenv, lo_v) & ~(kGroup - 1);
           hi = min(len, (upper_bound_gt(sy, lenv, hi_v) + kGroup - 1) & ~(kGroup - 1));
         };
+        bool lane_done = false;
+        if constexpr (K1T > 0 && D <= 5) {
+          if (a.lane_scan > 0) {
+            // ---- per-lane windows.  A warp-wide window of the staged chunk (as in the path below) that holds at
+            //      most a.lane_scan slots is walked by every lane on its own (knn_scan_lane: only the slots inside
+            //      the lane's own coordinate-1 window are looked at); wider windows (sparse regions, where the
+            //      serial walk of one lane would hold up its warp) go through the all-lanes scan.
+            static_assert(NH == 1, "per-lane scan expects one home chunk per tile");
+            lane_done = true;
+            constexpr int kSeed = 8;             // slots on either side of the query's own slot that seed its list
+            const int lane_max = a.lane_scan;
+            auto scan_range = [&](int lenv, int lo, int hi, const bool (&want)[QPT]) {
+              // slots [lo, hi) of the staged chunk (multiples of kGroup; hi may reach into the NaN padding)
+              if (lo >= hi) return;
+              if (hi - lo > lane_max) {
+                if ((tid & 31) == 0) npairs += (unsigned long long)(hi - lo) * 32 * QPT;
+                knn_scan_chunk<D, K1T, TC, QPT>(sbuf, lo, hi, q, best, thr, heap);    // lanes that do not want the chunk lose nothing by looking
+              } else {
+#pragma unroll
+                for (int i = 0; i < QPT; ++i)
+                  if (want[i]) knn_scan_lane<D, K1T, TC, false>(sbuf, lo, min(hi, lenv), q[i], best[i], thr[i], -1, -1, npairs);
+              }
+            };
+            // L1. home chunk: seed every list from the query's own neighbourhood (consecutive in coordinate 1),
+            //     then the rest of the warp's neighbourhood per lane, then the rest of the warp window
+            {
+              const int j = home_lo;
+              const int len = fetch_chunk(j);
+              const int lenv = min(TC, tile.c_len - j * TC);
+              int ska[QPT], skb[QPT];
+#pragma unroll
+              for (int i = 0; i < QPT; ++i) {
+                const int so = (tile.q_lo - tile.c_lo) + qslot[i] - j * TC;     // own slot, chunk-relative
+                ska[i] = skb[i] = -1;
+                if (valid[i]) {
+                  ska[i] = max(so - kSeed, 0);
+                  skb[i] = min(so + kSeed + 1, lenv);
+                  knn_seed_lane<D, K1T, TC>(sbuf, ska[i], skb[i], q[i], best[i], thr[i], npairs);
+                }
+              }
+              if (warp_has) {
+                int lo = 0, hi = len;
+                if (lane_max < TC) window(j, len, lo, hi);
+                // the slots some lane of the warp has seeded from: always per lane (each lane skips its own seeds)
+                const int ua = max(lo, max(own_lo - j * TC - kSeed, 0) & ~(kGroup - 1));
+                const int ub = min(hi, (min(own_hi - j * TC + kSeed, len) + kGroup - 1) & ~(kGroup - 1));
+#pragma unroll
+                for (int i = 0; i < QPT; ++i)
+                  if (valid[i] && ua < ub)
+                    knn_scan_lane<D, K1T, TC, true>(sbuf, ua, min(ub, lenv), q[i], best[i], thr[i], ska[i], skb[i], npairs);
+                scan_range(lenv, lo, min(ua, hi), valid);
+                scan_range(lenv, max(ub, lo), hi, valid);
+              }
+              __syncthreads();
+            }
+            // L2. outwards over the chunks: same chunk-level rules as the all-lanes path below
+            for (int j = home_hi + 1; j < nchunks; ++j) {
+              const double cmin = a.cell_lo[j];
+              bool need[QPT], any_need = false;
+#pragma unroll
+              for (int i = 0; i < QPT; ++i) { need[i] = valid[i] && !((cmin - q[i][0]) >= thr[i]); any_need = any_need || need[i]; }
+              const bool wneed = __any_sync(0xffffffffu, any_need);
+              const int nneed = __syncthreads_count(any_need);
+              if (nneed == 0) break;
+              if (nneed < a.defer_below) {
+#pragma unroll
+                for (int i = 0; i < QPT; ++i)
+                  if (need[i]) rstart[i] = j * TC;
+                break;
+              }
+              const int len = fetch_chunk(j);
+              if (wneed) {
+                int lo = 0, hi = len;
+                if (lane_max < TC) window(j, len, lo, hi);
+                scan_range(min(TC, tile.c_len - j * TC), lo, hi, need);
+              }
+            }
+            __syncthreads();
+            for (int j = home_lo - 1; j >= 0; --j) {
+              const double cmax = a.cell_hi[j];
+              bool need[QPT], any_need = false;
+#pragma unroll
+              for (int i = 0; i < QPT; ++i) { need[i] = valid[i] && !((q[i][0] - cmax) >= thr[i]); any_need = any_need || need[i]; }
+              const bool wneed = __any_sync(0xffffffffu, any_need);
+              const int nneed = __syncthreads_count(any_need);
+              if (nneed == 0) break;
+              if (nneed < a.defer_below) {
+#pragma unroll
+                for (int i = 0; i < QPT; ++i)
+                  if (need[i]) lend[i] = min((j + 1) * TC, tile.c_len);
+                break;
+              }
+              const int len = fetch_chunk(j);
+              if (wneed) {
+                int lo = 0, hi = len;
+                if (lane_max < TC) window(j, len, lo, hi);
+                scan_range(min(TC, tile.c_len - j * TC), lo, hi, need);
+              }
+            }
+            __syncthreads();
+          }
+        }
+        if (!lane_done) {
         int sa[NH], sb[NH];
         // 1a. seed every list from the warp's own neighbourhood in its home chunk(s)
 #pragma unroll
@@ -482,6 +666,7 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(D, K1T, QPT)) knn_ker
           }
         }
         __syncthreads();
+        }
       }
     } else {
       // 1. the chunks that overlap the tile itself: seeds every list with near neighbours

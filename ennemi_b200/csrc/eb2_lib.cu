@@ -366,9 +366,24 @@ struct TileSet {
 TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_hi, bool self, int c_lo, int c_len) {
   std::vector<Tile> t;
   int64_t rank = 0, rows = 0;
+  // two-level layout: the chunks at the two ends of the across-chunk coordinate lie in sparse regions, all their
+  // queries search wide windows over several chunks and their CTAs would form the tail of the kernel: split them
+  // into quarter tiles so that the work spreads over four times as many SMs
+  int edge_chunks = 0;
+  if (self && ps.cell_lo && ps.seg_slot.size() == 1) {
+    const int nch = cdiv(ps.seg_len[0], chunk_len(ps.cell_dim));
+    edge_chunks = 1;
+    if (const char* e = getenv("EB2_EDGE_CHUNKS")) edge_chunks = atoi(e);     // tuning knob
+  }
   for (size_t g = 0; g < ps.seg_slot.size(); ++g) {
-    const int tq = tile_rows(ps.qpt);
+    const int tq_full = tile_rows(ps.qpt);
+    int tq = tq_full;
     for (int off = 0; off < ps.seg_len[g]; off += tq) {
+      tq = tq_full;
+      if (edge_chunks > 0) {
+        const int tc = chunk_len(ps.cell_dim), ch = off / tc, nch = cdiv(ps.seg_len[g], tc);
+        if (ch < edge_chunks || ch >= nch - edge_chunks) tq = tq_full / 4;
+      }
       const int qn = std::min(tq, ps.seg_len[g] - off);
       if (rank >= row_lo && rank < row_hi) {
         Tile x;
@@ -445,7 +460,7 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
   a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
   const int k1t = (k + 1 <= 4) ? 4 : 8;
   if (a.sort_row >= 0 && k + 1 <= 8) {
-    a.defer_below = a.cell_lo ? 8 : 16;      // measured optima (tools/exp_defer.py)
+    a.defer_below = a.cell_lo ? (D <= 2 ? 4 : 8) : 16;      // measured optima (tools/exp_defer.py, tools/exp_knobs.py)
     if (const char* e = getenv("EB2_DEFER")) a.defer_below = atoi(e);     // tuning knob
   }
   if (a.defer_below > 0) {
@@ -454,6 +469,10 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
     a.left_best = s.dev<double>(static_cast<size_t>(ps.stride) * k1t);
     CU(cudaMemsetAsync(a.left_count, 0, sizeof(unsigned int), s.c.stream));
   }
+  int lane_dim = 5;
+  if (const char* e = getenv("EB2_LANE_DIM")) lane_dim = atoi(e);                          // tuning knob
+  a.lane_scan = (a.cell_lo && k + 1 <= 8 && D <= lane_dim && D <= 5) ? (1 << 30) : 0;
+  if (const char* e = getenv("EB2_LANE_SCAN")) a.lane_scan = a.lane_scan ? atoi(e) : 0;   // tuning knob (0 = off)
   const int grid = knn_grid(k, ts.count, s.c.sm_count);
   if (k + 1 > 8) a.heap = s.dev<double>(static_cast<size_t>(k + 1) * grid * tile_rows(ps.qpt));
   CU(launch_knn(D, ps.qpt, a, grid, s.c.stream));
