@@ -43,7 +43,7 @@ def use(dev: int):
         _tls.dev = prev
 
 
-LANES = 3    # concurrent streams per GPU used by the task fan-out (the library supports up to 4)
+LANES = 4    # concurrent streams per GPU used by the task fan-out (all the library has: measured best for pairwise_mi)
 
 
 def ordinal(dev: int) -> int:

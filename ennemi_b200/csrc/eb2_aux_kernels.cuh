@@ -159,7 +159,13 @@ struct GatherArgs {
 
 __global__ void gather_kernel(const GatherArgs a) {
   const int64_t rank = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (rank >= a.n) return;
+  if (rank >= a.n) {
+    if (!a.cls_sorted && rank < a.stride) {        // single segment: the padding slots after the last row
+      for (int t = 0; t < a.d; ++t) a.P[t * a.stride + rank] = __longlong_as_double(0x7ff8000000000000LL);
+      a.slot_row[rank] = -1;
+    }
+    return;
+  }
   const int row = a.perm ? a.perm[rank] : (int)rank;
   int64_t slot = rank;
   if (a.cls_sorted) {
@@ -168,6 +174,26 @@ __global__ void gather_kernel(const GatherArgs a) {
   }
   for (int t = 0; t < a.d; ++t) a.P[t * a.stride + slot] = a.rows[t][row];
   a.slot_row[slot] = row;
+}
+
+// two-level layout by partition (build_point_set_rows): chunk of every row from its rank in coordinate 0 ...
+__global__ void row_chunk_kernel(const int* __restrict__ perm0, int n, int tc, int* __restrict__ row_chunk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) row_chunk[perm0[i]] = i / tc;
+}
+// ... read in the order of coordinate 1 (a stable sort of these keys then lists every chunk's rows in that order)
+__global__ void chunk_key_kernel(const int* __restrict__ perm1, const int* __restrict__ row_chunk, int n, int* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = row_chunk[perm1[i]];
+}
+// range of coordinate 0 per chunk, from its ascending values
+__global__ void cell_bounds_kernel(const double* __restrict__ keys0, long long n, int tc, int nchunks, double* lo, double* hi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const long long a = (long long)c * tc;
+  const long long b = (a + tc < n ? a + tc : n) - 1;
+  lo[c] = keys0[a];
+  hi[c] = keys0[b];
 }
 
 __global__ void gather_int_kernel(const int* src, const int* perm, int* dst, int n) {

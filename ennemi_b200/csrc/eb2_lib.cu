@@ -23,6 +23,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -101,6 +102,14 @@ struct Ctx {
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
   DevShared* shared = nullptr;
+  // per-call workspace: one block per lane, bump-allocated by Scratch and kept across calls (calls on a lane are
+  // serialised and stream-ordered, so the next call may reuse it); grown after a call that did not fit
+  char* arena = nullptr;
+  size_t arena_cap = 0;
+  // tile tables of recent single-segment layouts (same n, same options => same table: every pair of a pairwise_mi call)
+  struct TileEntry { int64_t key[8]; void* dev; int count; int64_t rows; };
+  std::vector<TileEntry> tile_cache;
+  bool timing = true;                 // per-phase CUDA events (skipped inside batched calls)
   // NumPy pairwise-summation tables of the most recent window lengths (device copies; allocated and used on `stream`)
   struct NpTables { int64_t n; void* leaves; void* children; int nleaves, ninner; NpLevels levels; };
   std::vector<NpTables> np_tables;
@@ -160,12 +169,28 @@ struct Scratch {
   explicit Scratch(Ctx& ctx) : c(ctx) {}
   std::vector<void*> extra_pinned;
   bool used_side = false;     // work was forked to the second stream: it must finish before buffers are released
+  size_t arena_used = 0, overflow = 0;
+  double* result = nullptr;   // device block of the call: [0..3] reduction output, [4] pair counter (u64), [5] data flags (int)
   ~Scratch() {
     if (used_side) {
       cudaEventRecord(c.join, c.side);
       cudaStreamWaitEvent(c.stream, c.join, 0);
     }
     for (void* p : ptrs) cudaFreeAsync(p, c.stream);
+    if (overflow) {
+      // the call did not fit into the lane's workspace: replace it by one that would have held everything
+      if (c.arena) cudaFreeAsync(c.arena, c.stream);
+      c.arena = nullptr;
+      c.arena_cap = 0;
+      const size_t want = (arena_used + overflow) + (arena_used + overflow) / 4 + (1 << 20);
+      void* p = nullptr;
+      if (cudaMallocAsync(&p, want, c.stream) == cudaSuccess) {
+        c.arena = static_cast<char*>(p);
+        c.arena_cap = want;
+      } else {
+        cudaGetLastError();
+      }
+    }
     if (!extra_pinned.empty()) {
       cudaStreamSynchronize(c.stream);
       for (void* p : extra_pinned) cudaFreeHost(p);
@@ -173,9 +198,16 @@ struct Scratch {
   }
   template <typename T>
   T* dev(size_t count) {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+    if (arena_used + bytes <= c.arena_cap) {
+      T* p = reinterpret_cast<T*>(c.arena + arena_used);
+      arena_used += bytes;
+      return p;
+    }
     void* p = nullptr;
-    CU(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), c.stream));
+    CU(cudaMallocAsync(&p, bytes, c.stream));
     ptrs.push_back(p);
+    overflow += bytes;
     return static_cast<T*>(p);
   }
   // pinned staging slice (valid until the call ends)
@@ -223,6 +255,23 @@ void sort_pairs(Scratch& s, const K* kin, K* kout, const V* vin, V* vout, int n,
   CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, n, begin_bit, end_bit, s.c.stream));
 }
 
+// the same sort on the context's second stream, concurrent with whatever the main stream does next; every
+// buffer must have been allocated (and its inputs produced) on the main stream before the call.  The caller
+// joins with side_join() before the results are used.
+template <typename K, typename V>
+void sort_pairs_side(Scratch& s, const K* kin, K* kout, const V* vin, V* vout, int n, int begin_bit, int end_bit) {
+  Ctx& c = s.c;
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin, kout, vin, vout, n, begin_bit, end_bit, c.side));
+  void* tmp = s.dev<char>(tmp_bytes);
+  s.used_side = true;
+  CU(cudaEventRecord(c.fork, c.stream));
+  CU(cudaStreamWaitEvent(c.side, c.fork, 0));
+  CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, n, begin_bit, end_bit, c.side));
+  CU(cudaEventRecord(c.join, c.side));
+}
+void side_join(Scratch& s) { CU(cudaStreamWaitEvent(s.c.stream, s.c.join, 0)); }
+
 void sort_keys(Scratch& s, const double* kin, double* kout, int n) {
   size_t tmp_bytes = 0;
   CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, kin, kout, n, 0, 64, s.c.stream));
@@ -239,7 +288,7 @@ struct Presorted {
 };
 PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, int64_t n, const int* cls,
                               const std::vector<int>& class_size, int sort_row, int cell_dim, int cell_row2,
-                              const Presorted* pre);
+                              const Presorted* pre, const Presorted* pre2 = nullptr, bool pre2_on_side = false);
 
 PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const int* cls,
                          const std::vector<int>& class_size, int sort_row, int cell_dim = 0, int cell_row2 = -1) {
@@ -248,9 +297,12 @@ PointSet build_point_set(Scratch& s, const double* raw, int d, int64_t n, const 
   return build_point_set_rows(s, rows, d, n, cls, class_size, sort_row, cell_dim, cell_row2, nullptr);
 }
 
+// pre / pre2: row `sort_row` / row `cell_row2` already sorted (ascending values + rank -> row).  With both, the
+// two-level layout is built by PARTITION instead of per-chunk sorts: the rows are read in the order of coordinate 1
+// and stably radix-sorted by their chunk (rank in coordinate 0 / chunk length): 9 key bits at N = 10^6.
 PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, int64_t n, const int* cls,
                               const std::vector<int>& class_size, int sort_row, int cell_dim, int cell_row2,
-                              const Presorted* pre) {
+                              const Presorted* pre, const Presorted* pre2, bool pre2_on_side) {
   cudaStream_t st = s.c.stream;
   PointSet ps;
   ps.d = d;
@@ -321,10 +373,40 @@ PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, i
     cls_sorted = cls_out;
   }
 
+  const bool want_cells = cell_dim >= 2 && cell_dim <= kMaxDim && cell_row2 >= 0 && sort_row >= 0 && !cls && !getenv("EB2_NO_CELLS");
+  bool cells_done = false;
+  if (want_cells && pre2 && perm && !getenv("EB2_CELL_SORT")) {
+    const int tc = chunk_len(cell_dim);
+    const int nchunks = cdiv(n, tc);
+    int* row_chunk = s.dev<int>(n);
+    int* keys = s.dev<int>(n);
+    int* keys_out = s.dev<int>(n);
+    int* order = s.dev<int>(n);
+    row_chunk_kernel<<<blocks_n, 256, 0, st>>>(perm, static_cast<int>(n), tc, row_chunk);
+    if (pre2_on_side) side_join(s);
+    chunk_key_kernel<<<blocks_n, 256, 0, st>>>(pre2->perm, row_chunk, static_cast<int>(n), keys);
+    s.launches += 2;
+    int bits = 1;
+    while ((1 << bits) < nchunks && bits < 31) ++bits;
+    sort_pairs<int, int>(s, keys, keys_out, pre2->perm, order, static_cast<int>(n), 0, bits);
+    perm = order;
+    ps.cell_dim = cell_dim;
+    ps.cell_row2 = cell_row2;
+    ps.cell_lo = s.dev<double>(nchunks);
+    ps.cell_hi = s.dev<double>(nchunks);
+    cell_bounds_kernel<<<cdiv(nchunks, 256), 256, 0, st>>>(ps.sorted_keys, n, tc, nchunks, ps.cell_lo, ps.cell_hi);
+    s.launches++;
+    cells_done = true;
+  } else if (pre2 && pre2_on_side) {
+    side_join(s);
+  }
+
   ps.P = s.dev<double>(static_cast<size_t>(d) * ps.stride);
   ps.slot_row = s.dev<int>(ps.stride);
-  CU(cudaMemsetAsync(ps.P, 0xFF, sizeof(double) * d * ps.stride, st));     // all-ones = NaN
-  CU(cudaMemsetAsync(ps.slot_row, 0xFF, sizeof(int) * ps.stride, st));     // -1
+  if (cls) {     // (single-segment sets: the gather kernel writes the few padding slots itself)
+    CU(cudaMemsetAsync(ps.P, 0xFF, sizeof(double) * d * ps.stride, st));     // all-ones = NaN
+    CU(cudaMemsetAsync(ps.slot_row, 0xFF, sizeof(int) * ps.stride, st));     // -1
+  }
   GatherArgs ga;
   for (int t = 0; t < d; ++t) ga.rows[t] = row_src[t];
   ga.n = n; ga.d = d; ga.perm = perm; ga.cls_sorted = cls_sorted;
@@ -339,10 +421,10 @@ PointSet build_point_set_rows(Scratch& s, const double* const* row_src, int d, i
     ga.seg_slot = dv + nseg;
   }
   ga.P = ps.P; ga.stride = ps.stride; ga.slot_row = ps.slot_row;
-  gather_kernel<<<blocks_n, 256, 0, st>>>(ga);
+  gather_kernel<<<cdiv(cls ? n : ps.stride, 256), 256, 0, st>>>(ga);
   s.launches++;
   CU(cudaGetLastError());
-  if (cell_dim >= 2 && cell_dim <= kMaxDim && cell_row2 >= 0 && sort_row >= 0 && !cls && !getenv("EB2_NO_CELLS")) {
+  if (want_cells && !cells_done) {
     const int tc = chunk_len(cell_dim);
     const int nchunks = cdiv(n, tc);
     ps.cell_dim = cell_dim;
@@ -371,9 +453,26 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
   // into quarter tiles so that the work spreads over four times as many SMs
   int edge_chunks = 0;
   if (self && ps.cell_lo && ps.seg_slot.size() == 1) {
-    const int nch = cdiv(ps.seg_len[0], chunk_len(ps.cell_dim));
     edge_chunks = 1;
     if (const char* e = getenv("EB2_EDGE_CHUNKS")) edge_chunks = atoi(e);     // tuning knob
+  }
+  // the table of a single-segment layout depends only on these numbers: reuse the device copy of an earlier call
+  int64_t ckey[8] = {ps.seg_len.empty() ? 0 : ps.seg_len[0], ps.seg_slot.empty() ? 0 : ps.seg_slot[0], ps.qpt, row_lo, row_hi,
+                     (self ? 1 : 0) | (ps.sort_row >= 0 ? 2 : 0) | (static_cast<int64_t>(edge_chunks) << 8) |
+                         (static_cast<int64_t>(ps.cell_lo ? ps.cell_dim : 0) << 40),
+                     c_lo, c_len};
+  const bool cacheable = ps.seg_slot.size() == 1;
+  if (cacheable) {
+    for (size_t i = 0; i < s.c.tile_cache.size(); ++i) {
+      if (std::memcmp(s.c.tile_cache[i].key, ckey, sizeof ckey) == 0) {
+        Ctx::TileEntry e = s.c.tile_cache[i];
+        s.c.tile_cache.erase(s.c.tile_cache.begin() + i);
+        s.c.tile_cache.push_back(e);                      // most recently used last
+        TileSet hit;
+        hit.dev = static_cast<Tile*>(e.dev); hit.count = e.count; hit.rows = e.rows;
+        return hit;
+      }
+    }
   }
   for (size_t g = 0; g < ps.seg_slot.size(); ++g) {
     const int tq_full = tile_rows(ps.qpt);
@@ -414,8 +513,24 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
   if (ts.count) {
     Tile* h = s.host<Tile>(t.size());
     std::memcpy(h, t.data(), sizeof(Tile) * t.size());
-    ts.dev = s.dev<Tile>(t.size());
+    if (cacheable) {
+      void* p = nullptr;
+      CU(cudaMallocAsync(&p, sizeof(Tile) * t.size(), s.c.stream));      // outlives the call (freed on eviction / shutdown)
+      ts.dev = static_cast<Tile*>(p);
+    } else {
+      ts.dev = s.dev<Tile>(t.size());
+    }
     CU(cudaMemcpyAsync(ts.dev, h, sizeof(Tile) * t.size(), cudaMemcpyHostToDevice, s.c.stream));
+    if (cacheable) {
+      if (s.c.tile_cache.size() >= 12) {
+        cudaFreeAsync(s.c.tile_cache.front().dev, s.c.stream);
+        s.c.tile_cache.erase(s.c.tile_cache.begin());
+      }
+      Ctx::TileEntry e;
+      std::memcpy(e.key, ckey, sizeof ckey);
+      e.dev = ts.dev; e.count = ts.count; e.rows = ts.rows;
+      s.c.tile_cache.push_back(e);
+    }
   }
   return ts;
 }
@@ -561,8 +676,11 @@ void run_search(Scratch& s, const double* qcoord, const double* radius, const do
 
 // per-tile digamma partials -> 4 doubles on the device
 double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* cc, const double* dist, const TileSet& ts) {
-  double* out4 = s.dev<double>(4);
-  CU(cudaMemsetAsync(out4, 0, sizeof(double) * 4, s.c.stream));
+  double* out4 = s.result;              // zeroed by begin_call
+  if (!out4) {
+    out4 = s.dev<double>(4);
+    CU(cudaMemsetAsync(out4, 0, sizeof(double) * 4, s.c.stream));
+  }
   if (!ts.count) return out4;
   PsiArgs a;
   a.cnt_a = ca; a.cnt_b = cb; a.cnt_c = cc; a.dist = dist; a.tiles = ts.dev; a.ntiles = ts.count; a.mode = mode;
@@ -832,22 +950,32 @@ void export_outputs(Scratch& s, const PointSet& ps, const double* eps, const int
 }
 
 // gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
+thread_local bool g_skip_timing = false;   // set by batched calls for all but their last task
+
 int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs, const int* nonfinite, int64_t rows,
                 double* partial) {
   Ctx& c = s.c;
   struct Res { double v[4]; unsigned long long pairs; int nonfinite; };
   Res* h = s.host<Res>(1);
-  CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
-  CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-  CU(cudaMemcpyAsync(&h->nonfinite, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  CU(cudaEventRecord(c.ev[5], c.stream));
+  static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40, "Res mirrors the device result block");
+  if (out4 == s.result && s.result) {
+    CU(cudaMemcpyAsync(h, s.result, 44, cudaMemcpyDeviceToHost, c.stream));     // the whole block in one copy
+  } else {
+    CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(&h->nonfinite, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  }
+  const bool timing = !g_skip_timing;
+  if (timing) CU(cudaEventRecord(c.ev[5], c.stream));
   CU(cudaStreamSynchronize(c.stream));
-  float ms = 0;
-  CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[5])); c.last_ms[0] = ms;
-  CU(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2])); c.last_ms[1] = ms;
-  CU(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3])); c.last_ms[2] = ms;
-  CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
-  CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
+  if (timing) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[5])); c.last_ms[0] = ms;
+    CU(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2])); c.last_ms[1] = ms;
+    CU(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3])); c.last_ms[2] = ms;
+    CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
+    CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
+  }
   c.last_launches = s.launches;
   if (h->nonfinite & 8) {
     g_data_flags = h->nonfinite;
@@ -877,15 +1005,17 @@ struct CallInit {
 CallInit begin_call(Scratch& s) {
   Ctx& c = s.c;
   CU(cudaSetDevice(c.dev));
-  CU(cudaEventRecord(c.ev[0], c.stream));
+  if (!g_skip_timing) CU(cudaEventRecord(c.ev[0], c.stream));
   CallInit ci;
-  ci.pairs = s.dev<unsigned long long>(1);
-  ci.nonfinite = s.dev<int>(1);
-  CU(cudaMemsetAsync(ci.pairs, 0, sizeof(unsigned long long), c.stream));
-  CU(cudaMemsetAsync(ci.nonfinite, 0, sizeof(int), c.stream));
+  s.result = s.dev<double>(8);
+  CU(cudaMemsetAsync(s.result, 0, sizeof(double) * 8, c.stream));
+  ci.pairs = reinterpret_cast<unsigned long long*>(s.result + 4);
+  ci.nonfinite = reinterpret_cast<int*>(s.result + 5);
   return ci;
 }
-void mark(Scratch& s, int ev) { CU(cudaEventRecord(s.c.ev[ev], s.c.stream)); }
+void mark(Scratch& s, int ev) {
+  if (!g_skip_timing) CU(cudaEventRecord(s.c.ev[ev], s.c.stream));
+}
 
 // host copy of the reference's _psi for scalars (_entropy_estimators.py:327-350)
 double psi_host(double y) {
@@ -992,6 +1122,12 @@ int eb2_shutdown(void) {
       for (auto& kv : c.shared->cache) cudaFreeAsync(kv.second.first, c.stream);
       c.shared->cache.clear();
     }
+    if (c.arena) cudaFreeAsync(c.arena, c.stream);
+    c.arena = nullptr; c.arena_cap = 0;
+    for (auto& te : c.tile_cache) cudaFreeAsync(te.dev, c.stream);
+    c.tile_cache.clear();
+    for (auto& tb : c.np_tables) { cudaFreeAsync(tb.leaves, c.stream); cudaFreeAsync(tb.children, c.stream); }
+    c.np_tables.clear();
     cudaStreamSynchronize(c.stream);
     for (auto& e : c.ev) cudaEventDestroy(e);
     cudaEventDestroy(c.fork); cudaEventDestroy(c.join);
@@ -1169,12 +1305,23 @@ int eb2_mi_cols_batch(int dev, const eb2_col_t* cols, int64_t ntasks, int c_dim,
   const int d = 2 + c_dim;
   for (int64_t t = 0; t < ntasks; ++t) {
     g_data_flags = 0;
+    g_skip_timing = t + 1 < ntasks;      // eb2_last_timing reports the last task of the batch
     const int rc = c_dim == 0 ? eb2_ksg_mi_cols(dev, cols + t * d, n, k, flags, values + t)
                               : eb2_cmi_cols(dev, cols + t * d, n, c_dim, k, flags, values + t);
     status[t] = rc ? (rc | (g_data_flags << 8)) : 0;
     if (rc) values[t] = std::numeric_limits<double>::quiet_NaN();
   }
+  g_skip_timing = false;
   return EB2_OK;
+}
+
+// Two ways to order the slots of every chunk by the in-chunk coordinate: one CTA-wide bitonic sort per chunk
+// (cell_sort_kernel: 2 launches, ~40 us of a nearly empty GPU at N = 10^5) or a stable partition of the globally
+// sorted in-chunk coordinate by chunk (7 small launches, cheaper on the device from a few 10^5 rows on).  Small
+// estimates are bound by the host's launch rate, large ones by device time.
+int64_t partition_min_rows() {
+  if (const char* e = getenv("EB2_PARTITION_MIN")) return atoll(e);     // tuning knob
+  return 300000;
 }
 
 // ---- a1: KSG ------------------------------------------------------------------------------------
@@ -1188,6 +1335,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     const double* raw = nullptr;
     const Derived* dx = nullptr;
     const Derived* dy = nullptr;
+    const double* ys_direct = nullptr;
     PointSet ps;
     if (in.cols && prune && !(flags & (EB2_FLAG_BRUTE_COUNT | EB2_FLAG_SINGLE_USE | EB2_FLAG_DEVICE_STATS)) && !getenv("EB2_NO_DERIVED")) {
       // prepared variables (rescaled values + their ascending order) are shared by all tasks of the call
@@ -1197,15 +1345,33 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
       s.launches++;
       const double* rows[2] = {dx->vals, dy->vals};
       const Presorted pre{dx->sorted, dx->perm};
-      ps = build_point_set_rows(s, rows, 2, n, nullptr, {}, 0, 2, 1, &pre);
+      const Presorted pre2{dy->sorted, dy->perm};
+      ps = build_point_set_rows(s, rows, 2, n, nullptr, {}, 0, 2, 1, &pre, n >= partition_min_rows() ? &pre2 : nullptr);
     } else {
       raw = stage_input(s, in, 2, n, ci.nonfinite);
-      ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
+      if (prune && n >= partition_min_rows() && !(flags & EB2_FLAG_BRUTE_COUNT) && !getenv("EB2_NO_CELLS") && !getenv("EB2_CELL_SORT")) {
+        // x and y are sorted side by side on the two streams (value -> row); the two-level layout then is a stable
+        // partition of the y order by x chunk, and both ascending arrays serve the marginal searches afterwards
+        int* iota = s.dev<int>(n);
+        iota_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(iota, static_cast<int>(n));
+        s.launches++;
+        double* xk = s.dev<double>(n); int* xp = s.dev<int>(n);
+        double* yk = s.dev<double>(n); int* yp = s.dev<int>(n);
+        sort_pairs_side<double, int>(s, raw + n, yk, iota, yp, static_cast<int>(n), 0, 64);
+        sort_pairs<double, int>(s, raw, xk, iota, xp, static_cast<int>(n), 0, 64);
+        const double* rows[2] = {raw, raw + n};
+        const Presorted pre{xk, xp};
+        const Presorted pre2{yk, yp};
+        ps = build_point_set_rows(s, rows, 2, n, nullptr, {}, 0, 2, 1, &pre, &pre2, true);
+        ys_direct = yk;
+      } else {
+        ps = build_point_set(s, raw, 2, n, nullptr, {}, prune ? 0 : -1, 2, 1);   // x across chunks, y inside
+      }
     }
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
-    // the ascending y needed by the n_y search does not depend on the k-NN pass: sort it on the second
-    // stream while the k-NN kernel runs (the sort kernels fill the SM time the k-NN tail leaves idle)
-    const double* ys = dy ? dy->sorted : nullptr;
+    // the ascending y needed by the n_y search: a by-product of the layout above, or (layouts without it) sorted on
+    // the second stream while the k-NN kernel runs
+    const double* ys = dy ? dy->sorted : ys_direct;
     bool forked = false;
     if (!ys && !(flags & EB2_FLAG_BRUTE_COUNT)) {
       double* t = s.dev<double>(n);
