@@ -13,6 +13,7 @@ namespace eb2 {
 struct SearchArgs {
   const double* qcoord;   // query coordinate per query slot
   const double* radius;   // per query slot
+  int from_eps;           // `radius` holds the k-th neighbour distances: the radius is fl(eps - 1e-12), taken here
   const double* sorted;   // ascending candidate coordinates
   // optional second marginal searched by the same launch (blockIdx.y == 1)
   const double* qcoord2;
@@ -31,19 +32,39 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchArgs a) {
   for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = a.tiles[tile_id];
     const double* s = sorted + tile.c_lo;
-    for (int qi = threadIdx.x; qi < tile.q_n; qi += kThreads) {
-      const int slot = tile.q_lo + qi;
-      const double x = qcoord[slot];
-      const double r = a.radius[slot];
+    for (int base = 0; base < tile.q_n; base += kThreads) {
+      const int qi = base + threadIdx.x;
+      const bool act = qi < tile.q_n;
+      const int slot = tile.q_lo + (act ? qi : 0);
+      const double x = act ? qcoord[slot] : 0.0;
+      const double r = act ? (a.from_eps ? a.radius[slot] - 1e-12 : a.radius[slot]) : 0.0;   // _entropy_estimators.py:109
+      // The queries of a warp are neighbours in the layout (same chunk of the across-chunk coordinate, consecutive in
+      // the in-chunk one), so their answers lie in a short stretch of `s`: two warp-uniform searches (broadcast loads)
+      // bracket it conservatively, the per-lane searches with the exact predicates run inside the bracket only.
+      const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+      double xmin = act ? x : kInf, xmax = act ? x : -kInf, rmax = act ? fmax(r, 0.0) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      }
+      int wl = 0, wh = tile.c_len;
+      if (xmin <= xmax) {
+        const double slack = 8.881784197001252e-16;  // 2^-50: the rounded per-lane tests can never disagree with the bracket
+        wl = lower_bound_ge(s, tile.c_len, (xmin - rmax) - (fabs(xmin) + rmax) * slack);
+        wh = upper_bound_gt(s, tile.c_len, (xmax + rmax) + (fabs(xmax) + rmax) * slack);
+      }
+      if (!act) continue;
       // first j with fl(x - s_j) <= r   (x - s_j is non-increasing in j)
-      int lo = 0, hi = tile.c_len;
+      int lo = wl, hi = wh;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if ((x - s[mid]) <= r) hi = mid; else lo = mid + 1;
       }
       const int first = lo;
       // first j with fl(s_j - x) > r    (s_j - x is non-decreasing in j)
-      lo = 0; hi = tile.c_len;
+      lo = wl; hi = wh;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if ((s[mid] - x) > r) hi = mid; else lo = mid + 1;

@@ -166,6 +166,10 @@ __device__ __forceinline__ int upper_bound_gt(const double* a, int len, double v
 template <int NQ>
 __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
   const int tid = threadIdx.x;
+  // With one compare-exchange per thread (blockDim >= NQ/2), the pairs of a stage with stride j <= 32 that fall
+  // into the 64-element block b are exactly those of warp b: such stages only need a warp barrier, unless the
+  // following stage has a longer stride (51 of the 66 stages of a 2,048-element sort).
+  const bool warp_local_ok = blockDim.x >= NQ / 2;
   for (int k = 2; k <= NQ; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int p = tid; p < NQ / 2; p += blockDim.x) {   // NQ/2 compare-exchanges per stage
@@ -178,9 +182,11 @@ __device__ __forceinline__ void cta_sort_keys(double* skey, int* sidx) {
           const int t = sidx[i]; sidx[i] = sidx[l]; sidx[l] = t;
         }
       }
-      __syncthreads();
+      const int next_j = (j > 1) ? (j >> 1) : k;
+      if (warp_local_ok && j <= 32 && next_j <= 32) __syncwarp(); else __syncthreads();
     }
   }
+  __syncthreads();
 }
 
 // moves one per-query double from its home thread to the thread that owns the query after sorting

@@ -664,9 +664,10 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
 
 // one or (qcoord2 != NULL) two 1-D marginals searched by one launch
 void run_search(Scratch& s, const double* qcoord, const double* radius, const double* sorted, const TileSet& ts, int* cnt,
-                const double* qcoord2 = nullptr, const double* sorted2 = nullptr, int* cnt2 = nullptr) {
+                const double* qcoord2 = nullptr, const double* sorted2 = nullptr, int* cnt2 = nullptr, bool from_eps = false) {
   if (!ts.count) return;
   SearchArgs a;
+  a.from_eps = from_eps ? 1 : 0;
   a.qcoord = qcoord; a.radius = radius; a.sorted = sorted; a.tiles = ts.dev; a.ntiles = ts.count; a.cnt = cnt;
   a.qcoord2 = qcoord2; a.sorted2 = sorted2; a.cnt2 = cnt2;
   search_kernel<<<dim3(ts.count, qcoord2 ? 2 : 1), kThreads, 0, s.c.stream>>>(a);
@@ -1391,8 +1392,10 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     double* radius = s.dev<double>(ps.stride);
     run_knn(s, ps, rows_range(0, 2), 2, k, self, eps, ci.pairs);
     mark(s, 2);
-    radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
-    s.launches++;
+    if (flags & EB2_FLAG_BRUTE_COUNT) {      // (the sort + search path takes the radius from eps itself)
+      radius_kernel<<<cdiv(ps.stride, 256), 256, 0, c.stream>>>(eps, radius, ps.stride);
+      s.launches++;
+    }
     if (forked) CU(cudaStreamWaitEvent(c.stream, c.join, 0));
     int* nx = s.dev<int>(ps.stride);
     int* ny = s.dev<int>(ps.stride);
@@ -1403,7 +1406,7 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
       const double* xs = ps.sorted_keys;             // x in ascending order, by-product of the layout sort
       if (!prune) { double* t = s.dev<double>(n); sort_keys(s, raw, t, (int)n); xs = t; }
       TileSet all = make_tiles(s, ps, row_lo, row_hi, false, 0, (int)n);
-      run_search(s, ps.P, radius, xs, all, nx, ps.P + ps.stride, ys, ny);
+      run_search(s, ps.P, eps, xs, all, nx, ps.P + ps.stride, ys, ny, true);
     }
     mark(s, 3);
     double* out4 = run_psi(s, PSI_AB, nx, ny, nullptr, nullptr, self);
