@@ -866,7 +866,16 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   const int k1 = a.k + 1;
   unsigned long long npairs = 0;
-  for (unsigned int e = blockIdx.x; e < nent; e += gridDim.x) {
+  // Two-level layout: most deferred queries still need a handful of chunks only - phase 0 gives each of them to ONE
+  // warp (no block barriers, eight queries in flight per CTA); the few that need more than kLight chunks, and all
+  // queries of one-level layouts, get a whole CTA in phase 1.
+  constexpr int kLight = 64;
+  const bool cells = (D >= 2) && a.cell_lo != nullptr;
+  for (int phase = cells ? 0 : 1; phase < 2; ++phase) {
+  const bool per_warp = phase == 0;
+  const unsigned int e_first = per_warp ? blockIdx.x * NW + warp : blockIdx.x;
+  const unsigned int e_step = per_warp ? gridDim.x * NW : gridDim.x;
+  for (unsigned int e = e_first; e < nent; e += e_step) {
     const LeftEntry le = a.left_list[e];
     double q[D];
 #pragma unroll
@@ -899,9 +908,11 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
         const double lo_v = (q[1] - gate) - (fabs(q[1]) + gate) * slack;
         const double hi_v = (q[1] + gate) + (fabs(q[1]) + gate) * slack;
         const int nr = r_hi - r_lo, nl = l_hi - l_lo;
+        if (((nr + nl) <= kLight) != per_warp) continue;      // the other phase's entry (uniform over the CTA in phase 1)
+        const int wi = per_warp ? 0 : warp, gw = per_warp ? 1 : NW;
         // batches of 32 chunks per warp: every lane binary-searches the coordinate-1 window of ITS chunk (the
         // 32 searches overlap their L2 latency), then the warp walks the non-empty windows together
-        for (int b0 = warp * 32; b0 < nr + nl; b0 += NW * 32) {
+        for (int b0 = wi * 32; b0 < nr + nl; b0 += gw * 32) {
           const int idx = b0 + lane;
           int wlo = 0, whi = 0, base = 0;
           if (idx < nr + nl) {
@@ -956,6 +967,19 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
         if (tid == 0) npairs += (unsigned long long)(en - b);
       }
     }
+    if (per_warp) {
+      // the list the main kernel left behind joins lane 0's (disjoint candidates), then one merge across the lanes
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < K1T; ++t) {
+          const double v = a.left_best[(int64_t)le.slot * K1T + t];
+          if (v < best[K1T - 1]) topk_insert<K1T>(best, v);
+        }
+      }
+      const double fin = warp_merge_lists<K1T>(best, k1);
+      if (lane == a.k) a.eps[le.slot] = fin;
+      continue;
+    }
     // per-warp merge -> shared; then warp 0 merges the NW warp lists and the stored list
     const double mine = warp_merge_lists<K1T>(best, K1T);
     if (lane < K1T) wlist[warp][lane] = mine;
@@ -969,6 +993,7 @@ __global__ void __launch_bounds__(kThreads) knn_leftover_kernel(const KnnArgs a)
       if (lane == a.k) a.eps[le.slot] = fin;
     }
     __syncthreads();
+  }
   }
   if (a.pairs && (tid & 31) == 0 && npairs) atomicAdd(a.pairs, npairs);
 }
