@@ -303,7 +303,7 @@ def run_gpu(args):
                     "pairs": 2016, "n": 100_000, "k": K_NEIGH, "scaling": "strong",
                     "max_offdiag_mi": float(np.nanmax(pw)),
                     "note": "ennemi_b200.pairwise_mi(data, k=3) on a host (100000, 64) array: columns cached on the "
-                            "GPU once, per-pair rescaling on the device, pair tasks on 3 stream lanes per GPU"
+                            "GPU once, per-pair rescaling on the device, pair tasks on 4 stream lanes per GPU"
                             + (", tasks dealt over the ranks + one all_gather" if world > 1 else "")}
         ebd.enable_task_fanout(False)
         ebd.enable_row_sharding(True)
@@ -332,7 +332,7 @@ def run_gpu(args):
         "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]); a step = one "
                                "estimate per GPU (N > 1: independent same-shape batches fanned out, no collective; the "
                                "row-sharded single estimate is in `sharded`)",
-                   "n": N_ROWS, "k": K_NEIGH, "algorithm": "exact two-level windowed all-pairs search (bit-exact eps and counts); brute force in brute_force",
+                   "n": N_ROWS, "k": K_NEIGH, "algorithm": "exact two-level search, per-lane window walk inside staged chunks (bit-exact eps and counts); brute force in brute_force",
                    "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
                    "parallelism": "single GPU" if world == 1 else f"task fan-out x{world} (+ rows/{world} in `sharded`)"},
         "mi": last["value"] if world == 1 else last["value_own"],
@@ -349,10 +349,11 @@ def run_gpu(args):
                      "survey_8d_frac": (float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR) / (knn_per_ms * 1e-3) * 1e-12 / peak,
                      "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
                              "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
-                             "ops = pairs actually evaluated x 4 (k-NN main + leftover kernels, ms_per_launch = both); the pruned search is "
-                             "latency/issue bound, not FP64 bound - survey_8d_frac is the same time against SURVEY.md 8(d)'s "
-                             "brute-force count N^2 x 4, which a pruned algorithm legitimately exceeds; the FP64 roofline proper is "
-                             "in brute_force"},
+                             "ops = pairs actually evaluated x 4 (k-NN main + leftover kernels, ms_per_launch = both); the default search "
+                             "looks at ~30 candidates per row (per-lane windows of the in-chunk coordinate) and is bound by shared-memory "
+                             "latency and per-chunk synchronisation, not by FP64 issue - survey_8d_frac is the same time against "
+                             "SURVEY.md 8(d)'s brute-force count N^2 x 4, which a pruned algorithm legitimately exceeds; the FP64 "
+                             "roofline proper (every pair evaluated) is in brute_force"},
         "clocks": clocks,
     }
     if sharded:

@@ -65,6 +65,28 @@ def launches():
         out.append(f"| `{name[:100]}` | {c} | {t:.3f} | {100 * t / tot:.1f}% |")
     return "\n".join(out), tot
 
+def one_step():
+    """Kernels of ONE default resident step (the launches from one nonfinite_kernel to the next psi_final_kernel
+    around a pruned knn_kernel launch), in launch order."""
+    path = os.path.join(ROOT, "gpurun_out", f"launches_{TAG}.csv")
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr, data = rows[hi], rows[hi + 1:]
+    ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    seq = [(r[ki].split("(")[0].replace("void ", ""), r[gi], float(r[vi].replace(",", "")) / 1e3) for r in data if len(r) > vi]
+    knn = [i for i, q in enumerate(seq) if "knn_kernel" in q[0] and q[2] < 5000.0]
+    if len(knn) < 3:
+        return ""
+    i0 = knn[2]
+    a = max(j for j in range(i0) if "nonfinite_kernel" in seq[j][0])
+    b = min(j for j in range(i0, len(seq)) if "psi_final_kernel" in seq[j][0])
+    out = ["| # | kernel | grid | us |", "|---|---|---|---|"]
+    for n, (name, grid, us) in enumerate(seq[a:b + 1]):
+        out.append(f"| {n} | `{name[:90]}` | {grid} | {us:.1f} |")
+    out.append(f"| | **sum** | | **{sum(q[2] for q in seq[a:b + 1]):.1f}** |")
+    return "\n".join(out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     subprocess.run(["cp", os.path.join(ROOT, "gpurun_out", f"launches_{TAG}.csv"), os.path.join(OUT, f"launches_{TAG}.csv")])
@@ -74,17 +96,20 @@ def main():
            f"`launches_{TAG}.csv` are the tracked copies.  Per-launch ncu times are cold-cache and serialised: compare shares.", "",
            "## Launch list of `bench.py --steps 2 --warmup 3 --no-cpu --no-pairwise` (resident, e2e and brute-force legs)", "",
            f"`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` — {tot:.1f} ms of kernels in total.", "", lt, "",
-           "The k-NN kernel is the step: everything else (CUB radix sort, binary-search counts, digamma reduction, layout) is a few per cent.", "",
+           "The brute-force leg (knn_kernel with EB2_FLAG_NO_PRUNE, 2 launches of ~273 ms) dominates the list; in the default step (resident and e2e legs) the k-NN kernels are about a third, the two 64-bit radix sorts another third, the marginal search a seventh.", "",
+           "## One default step (resident leg, N = 10^6, d = 2, k = 3), kernels in launch order", "",
+           "The y sort (second group of radix kernels, on the side stream) runs concurrently with the x sort in a real step; ncu serialises them.", "",
+           one_step(), "",
            "## Full captures", ""]
     doc.append(table(f"prof_knn_brute_{TAG}", "k-NN, brute force (EB2_FLAG_NO_PRUNE), N = 10^6, d = 2, k = 3",
                      "Every candidate chunk visited: 10^12 pairs, 4 x 10^12 FP64 instructions.  The FP64 pipe is the binding unit."))
-    doc.append(table(f"prof_knn_pruned_{TAG}", "k-NN, default (exact sorted-window pruning), N = 10^6, d = 2, k = 3",
-                     "Same kernel, pruned search: ~3.6 x 10^9 pairs.  Issue-slot and barrier bound (insert path + per-chunk synchronisation), not FP64 bound."))
+    doc.append(table(f"prof_knn_pruned_{TAG}", "k-NN, default (exact two-level search, per-lane window walk), N = 10^6, d = 2, k = 3",
+                     "Same kernel, default search: ~3 x 10^7 pairs (about 30 candidates per row) instead of 10^12.  Bound by shared-memory latency and per-chunk synchronisation (TMA round trip + block barrier per visited chunk), not by FP64 issue."))
     doc.append(table(f"prof_knn_leftover_{TAG}", "k-NN leftover kernel (deferred stragglers), same step",
-                     "One CTA per deferred query; candidate-parallel scan straight from L2."))
+                     "One warp per deferred query that needs at most 64 more chunks, a CTA for the rest; coordinate-1 windows searched and scanned straight from L2."))
     doc.append(table(f"prof_count_cmi_{TAG}", "marginal counts, Frenzel-Pompe (count_kernel<3,2>), N = 200,000, 3-D condition",
                      "n_z, n_xz, n_yz in one pass over candidates windowed in z_0."))
-    doc.append(table(f"prof_search_{TAG}", "1-D marginal counts (search_kernel), N = 10^6", "Binary search with the exact rounded-subtraction predicate; L2-latency bound."))
+    doc.append(table(f"prof_search_{TAG}", "1-D marginal counts (search_kernel), N = 10^6", "Two warp-uniform bracketing searches, then per-lane binary searches with the exact rounded-subtraction predicates; L2-latency bound."))
     open(os.path.join(OUT, f"ncu_{TAG}_summary.md"), "w").write("\n".join(doc))
     print("wrote", os.path.join(OUT, f"ncu_{TAG}_summary.md"))
 
