@@ -46,7 +46,7 @@ FP64_OPS_PER_PAIR = 4          # 2-D space: 2 subtractions + 2 compares (SURVEY.
 SAMPLE_STRIDE = 50             # CPU baseline: every 50th row is queried, trees hold all rows
 # dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel<2,4> at this workload, one ncu --set full capture
 # (profiles/ncu_r01_summary.md): the 16 MB point set is read once, everything else stays in the 126 MB L2
-NCU_DRAM_BYTES_PER_LAUNCH = 16.4e6
+NCU_DRAM_BYTES_PER_LAUNCH = 16.7e6
 
 
 def make_data(n=N_ROWS, seed=0):
@@ -107,7 +107,7 @@ def run_reference(args):
                                    f"every {SAMPLE_STRIDE}th row scaled x{SAMPLE_STRIDE}; single estimate = 1 thread in the reference"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -369,13 +369,38 @@ def run_gpu(args):
                                             "ops_per_launch": b_ops}}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_block(xs, ys, 1)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """Rank 0 prints exactly ONE line on stdout.  Libraries write there too (NCCL prints its version banner
+    from C code at communicator creation whatever NCCL_DEBUG says), so file descriptor 1 is pointed at stderr for
+    the duration of the run and the JSON line goes to the saved original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    payload = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(payload.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, payload)
+
+
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
