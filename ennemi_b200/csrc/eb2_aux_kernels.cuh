@@ -88,7 +88,20 @@ struct PsiArgs {
   int ntiles;
   int mode;
   double* partial;        // [ntiles][4]: sum, zeros_a, zeros_b, zeros_c
+  const double* tab;      // tab[n] = psi_ref(n) for n < tab_n, filled by psi_table_kernel with the same device function
+  int tab_n;              // (so a lookup returns the very bits an evaluation would); 0: no table
 };
+
+__global__ void psi_table_kernel(double* tab, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tab[i] = i == 0 ? 0.0 : psi_ref((double)i);
+}
+
+// digamma of a positive count: most counts are small (the neighbourhood of a point holds a few thousand rows at
+// N = 10^6), so the two fp64 logs per row become two cached loads
+__device__ __forceinline__ double psi_count(const PsiArgs& a, int n) {
+  return n < a.tab_n ? a.tab[n] : psi_ref((double)n);
+}
 
 __global__ void __launch_bounds__(kThreads) psi_kernel(const PsiArgs a) {
   __shared__ double red[kThreads / 32];
@@ -107,14 +120,14 @@ __global__ void __launch_bounds__(kThreads) psi_kernel(const PsiArgs a) {
           // through the zero counters and contributes nothing to the finite sum.
           const int na = a.cnt_a[slot];
           double term = 0.0;
-          if (na == 0) za += 1.0; else term = psi_ref((double)na);
+          if (na == 0) za += 1.0; else term = psi_count(a, na);
           if (a.mode >= PSI_AB) {
             const int nb = a.cnt_b[slot];
-            if (nb == 0) zb += 1.0; else term = term + psi_ref((double)nb);
+            if (nb == 0) zb += 1.0; else term = term + psi_count(a, nb);
           }
           if (a.mode == PSI_AB_MINUS_C) {
             const int nc = a.cnt_c[slot];
-            if (nc == 0) zc += 1.0; else term = term - psi_ref((double)nc);
+            if (nc == 0) zc += 1.0; else term = term - psi_count(a, nc);
           }
           sum += term;
         }

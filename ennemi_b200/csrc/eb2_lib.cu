@@ -109,7 +109,7 @@ struct Ctx {
   // tile tables of recent single-segment layouts (same n, same options => same table: every pair of a pairwise_mi call)
   struct TileEntry { int64_t key[8]; void* dev; int count; int64_t rows; };
   std::vector<TileEntry> tile_cache;
-  bool timing = true;                 // per-phase CUDA events (skipped inside batched calls)
+  double* psi_tab = nullptr;          // psi_ref(n), n < kPsiTab, filled on first use on this lane's stream
   // NumPy pairwise-summation tables of the most recent window lengths (device copies; allocated and used on `stream`)
   struct NpTables { int64_t n; void* leaves; void* children; int nleaves, ninner; NpLevels levels; };
   std::vector<NpTables> np_tables;
@@ -685,6 +685,15 @@ double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* c
   if (!ts.count) return out4;
   PsiArgs a;
   a.cnt_a = ca; a.cnt_b = cb; a.cnt_c = cc; a.dist = dist; a.tiles = ts.dev; a.ntiles = ts.count; a.mode = mode;
+  constexpr int kPsiTab = 1 << 16;
+  if (!s.c.psi_tab && mode != LOG_DIST) {
+    void* p = nullptr;
+    CU(cudaMallocAsync(&p, sizeof(double) * kPsiTab, s.c.stream));       // kept until eb2_shutdown
+    s.c.psi_tab = static_cast<double*>(p);
+    psi_table_kernel<<<cdiv(kPsiTab, 256), 256, 0, s.c.stream>>>(s.c.psi_tab, kPsiTab);
+    s.launches++;
+  }
+  a.tab = s.c.psi_tab; a.tab_n = s.c.psi_tab ? kPsiTab : 0;
   a.partial = s.dev<double>(static_cast<size_t>(ts.count) * 4);
   psi_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(a);
   psi_final_kernel<<<1, kThreads, 0, s.c.stream>>>(a.partial, ts.count, out4);
@@ -1125,6 +1134,8 @@ int eb2_shutdown(void) {
     }
     if (c.arena) cudaFreeAsync(c.arena, c.stream);
     c.arena = nullptr; c.arena_cap = 0;
+    if (c.psi_tab) cudaFreeAsync(c.psi_tab, c.stream);
+    c.psi_tab = nullptr;
     for (auto& te : c.tile_cache) cudaFreeAsync(te.dev, c.stream);
     c.tile_cache.clear();
     for (auto& tb : c.np_tables) { cudaFreeAsync(tb.leaves, c.stream); cudaFreeAsync(tb.children, c.stream); }

@@ -324,3 +324,48 @@ def test_wide_spaces_generic_kernels(d, n, k):
     for key, arr in parts.items():
         assert np.array_equal(arr, want[key]), (d, key)
     assert close(value, want["value"])
+
+
+@pytest.mark.parametrize("dist", ["gauss", "student_t2", "ties_plus_noise"])
+def test_search_variants_agree_bit_for_bit(dist, monkeypatch):
+    """Every way the library can lay out and walk the two-level search gives the same eps and counts, bit for bit,
+    as the brute-force kernel: per-lane window walk (default) vs the all-lanes window scan (EB2_LANE_SCAN=0) vs
+    a hybrid (walk only narrow warp windows), layout by partition (default at this size) vs per-chunk sort
+    (EB2_CELL_SORT), quarter tiles at the edge chunks on / off, straggler deferral off / default / aggressive
+    (one-warp and whole-CTA leftover paths).  Sizes sit above the partition threshold (300,000 rows)."""
+    rng = np.random.default_rng(17)
+    n = 320_001
+    if dist == "gauss":
+        d = rng.multivariate_normal([0, 0], [[1, 0.8], [0.8, 1]], size=n)
+    elif dist == "student_t2":
+        d = rng.standard_t(2, size=(n, 2))
+    else:       # what ennemi's preprocessing makes of integer-valued data: clusters 1e-10 wide
+        d = rng.integers(0, 50, size=(n, 2)).astype(float) + rng.normal(0, 1e-10, size=(n, 2))
+    coords = nat.pack_coords([d[:, 0], d[:, 1]])
+    v_ref, ref = nat.ksg_mi(coords, 3, flags=nat.FLAG_NO_PRUNE | nat.FLAG_BRUTE_COUNT, details=True)
+    variants = [{}, {"EB2_LANE_SCAN": "0"}, {"EB2_LANE_SCAN": "96"}, {"EB2_CELL_SORT": "1"}, {"EB2_EDGE_CHUNKS": "0"},
+                {"EB2_EDGE_CHUNKS": "5"}, {"EB2_DEFER": "0"}, {"EB2_DEFER": "64"}, {"EB2_DEFER": "64", "EB2_LANE_SCAN": "0"},
+                {"EB2_PARTITION_MIN": "1000000000"}, {"EB2_NO_CELLS": "1"}]
+    for env in variants:
+        with monkeypatch.context() as m:
+            for key, val in env.items():
+                m.setenv(key, val)
+            value, got = nat.ksg_mi(coords, 3, details=True)
+        for key in ("eps", "nx", "ny"):
+            assert np.array_equal(got[key], ref[key]), (dist, env, key)
+        assert close(value, v_ref) or (np.isinf(value) and value == v_ref), (dist, env)
+
+
+def test_walk_variants_agree_in_wider_spaces(monkeypatch):
+    """3-D and 5-D spaces (k = 3 and k = 6: both register list lengths): per-lane walk vs all-lanes scan vs brute force."""
+    rng = np.random.default_rng(23)
+    for dims, n, k in ((3, 120_000, 3), (5, 60_000, 6), (4, 50_000, 7)):
+        x = rng.normal(size=(n, dims)) @ rng.normal(size=(dims, dims))
+        coords = nat.pack_coords([x])
+        _, ref = nat.entropy(coords, k, flags=nat.FLAG_NO_PRUNE, details=True)
+        for env in ({}, {"EB2_LANE_SCAN": "0"}, {"EB2_LANE_DIM": "2"}, {"EB2_DEFER": "0"}, {"EB2_DEFER": "100"}):
+            with monkeypatch.context() as m:
+                for key, val in env.items():
+                    m.setenv(key, val)
+                _, got = nat.entropy(coords, k, details=True)
+            assert np.array_equal(got["dist"], ref["dist"]), (dims, env)
