@@ -343,6 +343,7 @@ def run_gpu(args):
                 "mi": last.get("e2e")},
         "gpu_launches": int(launches),
         "phase_ms": phases,
+        "layout_roofline": layout_roofline(phases),
         "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
@@ -373,6 +374,26 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def layout_roofline(phases):
+    """The sort/partition phase against the HBM roofline (radix sorts count as bytes).  Algorithmic
+    bytes of one step: two 64-bit key + 32-bit index radix sorts (8 passes, each reads and writes 12 B per row), the
+    2-pass 32-bit chunk partition (8 B per row per pass, both ways) and the gather of two coordinate rows + row map."""
+    n = float(N_ROWS)
+    bytes_step = 2 * 8 * 2 * 12 * n + 2 * 2 * 8 * n + (2 * 8 + 4) * 2 * n
+    peak, src = 6528.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        pass
+    ms = phases.get("layout_ms") or float("nan")
+    achieved = bytes_step / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "phase": "layout (x and y radix sorts, chunk partition, gather)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "bytes_per_step": bytes_step, "ms": ms, "peak_source": src,
+            "note": "at N = 1e6 every radix pass is a ~17 us kernel of 174 CTAs: latency bound (decoupled look-back chain), the "
+                    "working set lives in L2; listed because this phase is now the largest of the default step"}
 
 
 _REAL_STDOUT = None
