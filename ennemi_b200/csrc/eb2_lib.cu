@@ -110,6 +110,24 @@ struct Ctx {
   struct TileEntry { int64_t key[8]; void* dev; int count; int64_t rows; };
   std::vector<TileEntry> tile_cache;
   double* psi_tab = nullptr;          // psi_ref(n), n < kPsiTab, filled on first use on this lane's stream
+  // CUDA graphs of repeated resident estimates (EB2_GRAPH=0 turns them off): the lane workspace gives a repeated same-shape call the
+  // same device addresses, so its ~45 launches can be replayed as one graph launch.  Entries die with the workspace
+  // or the tile tables they reference.
+  struct GraphEntry {
+    int64_t key[8];
+    cudaGraphExec_t exec = nullptr;
+    void* host_result = nullptr;      // pinned block the graph's last node copies the result into
+    int64_t rows = 0;
+    int launches = 0;
+    bool seen = false;                // ran eagerly once without outgrowing the workspace
+    bool failed = false;              // capture did not work for this signature: stay eager
+  };
+  std::vector<GraphEntry> graphs;
+  void drop_graphs() {
+    for (auto& g : graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
   // NumPy pairwise-summation tables of the most recent window lengths (device copies; allocated and used on `stream`)
   struct NpTables { int64_t n; void* leaves; void* children; int nleaves, ninner; NpLevels levels; };
   std::vector<NpTables> np_tables;
@@ -171,6 +189,7 @@ struct Scratch {
   bool used_side = false;     // work was forked to the second stream: it must finish before buffers are released
   size_t arena_used = 0, overflow = 0;
   double* result = nullptr;   // device block of the call: [0..3] reduction output, [4] pair counter (u64), [5] data flags (int)
+  Ctx::GraphEntry* capture = nullptr;    // the call is being captured into this entry (stream capture is active)
   ~Scratch() {
     if (used_side) {
       cudaEventRecord(c.join, c.side);
@@ -179,6 +198,7 @@ struct Scratch {
     for (void* p : ptrs) cudaFreeAsync(p, c.stream);
     if (overflow) {
       // the call did not fit into the lane's workspace: replace it by one that would have held everything
+      c.drop_graphs();                 // they reference the old workspace
       if (c.arena) cudaFreeAsync(c.arena, c.stream);
       c.arena = nullptr;
       c.arena_cap = 0;
@@ -204,6 +224,7 @@ struct Scratch {
       arena_used += bytes;
       return p;
     }
+    if (capture) throw CudaFail{cudaErrorMemoryAllocation, "workspace too small during graph capture", __LINE__};
     void* p = nullptr;
     CU(cudaMallocAsync(&p, bytes, c.stream));
     ptrs.push_back(p);
@@ -513,6 +534,7 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
   if (ts.count) {
     Tile* h = s.host<Tile>(t.size());
     std::memcpy(h, t.data(), sizeof(Tile) * t.size());
+    if (s.capture) throw CudaFail{cudaErrorInvalidValue, "tile table not cached during graph capture", __LINE__};
     if (cacheable) {
       void* p = nullptr;
       CU(cudaMallocAsync(&p, sizeof(Tile) * t.size(), s.c.stream));      // outlives the call (freed on eviction / shutdown)
@@ -523,6 +545,7 @@ TileSet make_tiles(Scratch& s, const PointSet& ps, int64_t row_lo, int64_t row_h
     CU(cudaMemcpyAsync(ts.dev, h, sizeof(Tile) * t.size(), cudaMemcpyHostToDevice, s.c.stream));
     if (cacheable) {
       if (s.c.tile_cache.size() >= 12) {
+        s.c.drop_graphs();             // a graph may reference the evicted table
         cudaFreeAsync(s.c.tile_cache.front().dev, s.c.stream);
         s.c.tile_cache.erase(s.c.tile_cache.begin());
       }
@@ -962,31 +985,11 @@ void export_outputs(Scratch& s, const PointSet& ps, const double* eps, const int
 // gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
 thread_local bool g_skip_timing = false;   // set by batched calls for all but their last task
 
-int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs, const int* nonfinite, int64_t rows,
-                double* partial) {
-  Ctx& c = s.c;
-  struct Res { double v[4]; unsigned long long pairs; int nonfinite; };
-  Res* h = s.host<Res>(1);
-  static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40, "Res mirrors the device result block");
-  if (out4 == s.result && s.result) {
-    CU(cudaMemcpyAsync(h, s.result, 44, cudaMemcpyDeviceToHost, c.stream));     // the whole block in one copy
-  } else {
-    CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
-    CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-    CU(cudaMemcpyAsync(&h->nonfinite, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  }
-  const bool timing = !g_skip_timing;
-  if (timing) CU(cudaEventRecord(c.ev[5], c.stream));
-  CU(cudaStreamSynchronize(c.stream));
-  if (timing) {
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[5])); c.last_ms[0] = ms;
-    CU(cudaEventElapsedTime(&ms, c.ev[1], c.ev[2])); c.last_ms[1] = ms;
-    CU(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3])); c.last_ms[2] = ms;
-    CU(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4])); c.last_ms[3] = ms;
-    CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1])); c.last_ms[4] = ms;
-  }
-  c.last_launches = s.launches;
+struct Res { double v[4]; unsigned long long pairs; int nonfinite; };
+static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40, "Res mirrors the device result block");
+
+// the synchronised result block -> error code / partial block
+int parse_result(const Res* h, int64_t rows, double* partial) {
   if (h->nonfinite & 8) {
     g_data_flags = h->nonfinite;
     return fail(EB2_ERR_CONSTANT, "a window with device-computed statistics is constant (std < 1e-20): "
@@ -1008,6 +1011,106 @@ int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs,
   return EB2_OK;
 }
 
+// phase times of the call that just completed on the lane's stream (events of a replayed graph are external
+// record nodes; should a driver refuse the query, the previous figures simply stay)
+void read_phase_times(Ctx& c) {
+  static const int pairs[5][2] = {{0, 5}, {1, 2}, {2, 3}, {3, 4}, {0, 1}};
+  for (int i = 0; i < 5; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev[pairs[i][0]], c.ev[pairs[i][1]]) == cudaSuccess) c.last_ms[i] = ms;
+    else cudaGetLastError();
+  }
+}
+
+void record_event(Scratch& s, cudaEvent_t ev) {
+  if (s.capture) CU(cudaEventRecordWithFlags(ev, s.c.stream, cudaEventRecordExternal));
+  else CU(cudaEventRecord(ev, s.c.stream));
+}
+
+// gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
+int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs, const int* nonfinite, int64_t rows,
+                double* partial) {
+  Ctx& c = s.c;
+  Res* h = s.host<Res>(1);
+  if (out4 == s.result && s.result) {
+    CU(cudaMemcpyAsync(h, s.result, 44, cudaMemcpyDeviceToHost, c.stream));     // the whole block in one copy
+  } else {
+    CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaMemcpyAsync(&h->nonfinite, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  }
+  const bool timing = !g_skip_timing;
+  if (timing) record_event(s, c.ev[5]);
+  if (s.capture) {
+    // everything above was recorded, not run: close the capture, keep the executable graph, run it once
+    Ctx::GraphEntry* ge = s.capture;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamEndCapture(c.stream, &graph));
+    s.capture = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) throw CudaFail{e, "cudaGraphInstantiate", __LINE__};
+    ge->exec = exec;
+    ge->host_result = h;
+    ge->rows = rows;
+    ge->launches = s.launches;
+    CU(cudaGraphLaunch(exec, c.stream));
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  if (timing) read_phase_times(c);
+  c.last_launches = s.launches;
+  return parse_result(h, rows, partial);
+}
+
+// replays the captured estimate: one launch, one synchronisation
+int graph_replay(Ctx& c, Ctx::GraphEntry& ge, double* partial) {
+  CU(cudaSetDevice(c.dev));
+  CU(cudaGraphLaunch(ge.exec, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  read_phase_times(c);
+  c.last_launches = ge.launches;
+  return parse_result(static_cast<const Res*>(ge.host_result), ge.rows, partial);
+}
+
+// closes a capture that went wrong (nothing was executed) and forgets the error
+void abort_capture(Ctx& c) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(c.stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+    cudaGraph_t graph = nullptr;
+    cudaStreamEndCapture(c.stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  cudaGetLastError();
+}
+
+bool graph_enabled() {
+  const char* e = getenv("EB2_GRAPH");      // EB2_GRAPH=0: always launch kernel by kernel
+  return !e || atoi(e) != 0;
+}
+
+// entry of this call signature in the lane's graph cache (created on first sight; most recently used last)
+Ctx::GraphEntry* graph_entry(Ctx& c, const int64_t (&key)[8]) {
+  for (size_t i = 0; i < c.graphs.size(); ++i) {
+    if (std::memcmp(c.graphs[i].key, key, sizeof key) == 0) {
+      if (i + 1 != c.graphs.size()) {
+        Ctx::GraphEntry e = c.graphs[i];
+        c.graphs.erase(c.graphs.begin() + i);
+        c.graphs.push_back(e);
+      }
+      return &c.graphs.back();
+    }
+  }
+  if (c.graphs.size() >= 4) {
+    if (c.graphs.front().exec) cudaGraphExecDestroy(c.graphs.front().exec);
+    c.graphs.erase(c.graphs.begin());
+  }
+  Ctx::GraphEntry e;
+  std::memcpy(e.key, key, sizeof key);
+  c.graphs.push_back(e);
+  return &c.graphs.back();
+}
+
 struct CallInit {
   unsigned long long* pairs;
   int* nonfinite;
@@ -1015,7 +1118,7 @@ struct CallInit {
 CallInit begin_call(Scratch& s) {
   Ctx& c = s.c;
   CU(cudaSetDevice(c.dev));
-  if (!g_skip_timing) CU(cudaEventRecord(c.ev[0], c.stream));
+  if (!g_skip_timing) record_event(s, c.ev[0]);
   CallInit ci;
   s.result = s.dev<double>(8);
   CU(cudaMemsetAsync(s.result, 0, sizeof(double) * 8, c.stream));
@@ -1024,7 +1127,7 @@ CallInit begin_call(Scratch& s) {
   return ci;
 }
 void mark(Scratch& s, int ev) {
-  if (!g_skip_timing) CU(cudaEventRecord(s.c.ev[ev], s.c.stream));
+  if (!g_skip_timing) record_event(s, s.c.ev[ev]);
 }
 
 // host copy of the reference's _psi for scalars (_entropy_estimators.py:327-350)
@@ -1136,6 +1239,7 @@ int eb2_shutdown(void) {
     c.arena = nullptr; c.arena_cap = 0;
     if (c.psi_tab) cudaFreeAsync(c.psi_tab, c.stream);
     c.psi_tab = nullptr;
+    c.drop_graphs();
     for (auto& te : c.tile_cache) cudaFreeAsync(te.dev, c.stream);
     c.tile_cache.clear();
     for (auto& tb : c.np_tables) { cudaFreeAsync(tb.leaves, c.stream); cudaFreeAsync(tb.children, c.stream); }
@@ -1341,9 +1445,26 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
                          double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
   const uint32_t flags = in.flags;
   return guarded(dev, [&](Ctx& c) {
-    Scratch s(c);
-    CallInit ci = begin_call(s);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    // Repeated resident estimates of one shape (unless EB2_GRAPH=0): the second call runs eagerly once the lane workspace has
+    // its final size, the third is captured into a CUDA graph, later ones replay it with one launch.
+    const bool graphable = graph_enabled() && !in.cols && (flags & EB2_FLAG_DEVICE_INPUT) && prune &&
+                           !(flags & EB2_FLAG_BRUTE_COUNT) && n >= partition_min_rows() && !getenv("EB2_NO_CELLS") &&
+                           !getenv("EB2_CELL_SORT") && !eps_out && !nx_out && !ny_out && partial && !g_skip_timing;
+    const int64_t gkey[8] = {static_cast<int64_t>(reinterpret_cast<intptr_t>(in.coords)), n, k, static_cast<int64_t>(flags), row_lo, row_hi,
+                             static_cast<int64_t>(reinterpret_cast<intptr_t>(c.arena)), static_cast<int64_t>(c.arena_cap)};
+    if (graphable) {
+      Ctx::GraphEntry* ge = graph_entry(c, gkey);
+      if (ge->exec) return graph_replay(c, *ge, partial);
+    }
+    auto run = [&](bool capture) -> int {
+    Scratch s(c);
+    if (capture) {
+      CU(cudaSetDevice(c.dev));
+      CU(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+      s.capture = graph_entry(c, gkey);
+    }
+    CallInit ci = begin_call(s);
     const double* raw = nullptr;
     const Derived* dx = nullptr;
     const Derived* dy = nullptr;
@@ -1425,7 +1546,28 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     const int* cnts[3] = {nx, ny, nullptr};
     Outputs o; o.eps = eps_out; o.cnt[0] = nx_out; o.cnt[1] = ny_out;
     export_outputs(s, ps, eps, cnts, o);
-    return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+    const int rc = finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
+    if (graphable && !capture && rc == EB2_OK && s.overflow == 0 && reinterpret_cast<intptr_t>(c.arena) == static_cast<intptr_t>(gkey[6]))
+      graph_entry(c, gkey)->seen = true;       // (looked up again: tile-table eviction may have emptied the cache)
+    return rc;
+    };
+    if (graphable) {
+      Ctx::GraphEntry* ge = graph_entry(c, gkey);
+      if (ge->seen && !ge->failed) {
+        try {
+          return run(true);
+        } catch (const CudaFail&) {         // capture is best effort: stay eager for this signature
+          abort_capture(c);
+          Ctx::GraphEntry* g2 = graph_entry(c, gkey);
+          if (g2->exec) { cudaGraphExecDestroy(g2->exec); g2->exec = nullptr; }
+          g2->failed = true;
+        } catch (...) {
+          abort_capture(c);
+          throw;
+        }
+      }
+    }
+    return run(false);
   });
 }
 
