@@ -61,8 +61,15 @@ def _worker(rank, world, port, out_dir):
     ebd.enable_task_fanout(True)
     pw = eb.pairwise_mi(x, callback=lambda i, j: seen.append((i, j)))
     lagged = eb.estimate_mi(x[:, 0], x[:, 1:3], lag=[0, 1, 2])
+    # the same calls on device-resident columns (the (n, nvar) array travels as one block per rank)
+    from ennemi_b200 import api
+    api.DEVICE_COLUMNS_MIN_ROWS = 0
+    pw_cols = eb.pairwise_mi(x)
+    lagged_cols = eb.estimate_mi(x[:, 0], x[:, 1:3], lag=[0, 1, 2])
+    api.DEVICE_COLUMNS_MIN_ROWS = 10 ** 9
     ebd.enable_task_fanout(False)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), sharded=sharded, want=full["value"], pw=pw, lagged=lagged,
+             pw_cols=pw_cols, lagged_cols=lagged_cols, block_puts=getattr(fake, "block_puts", 0),
              seen=np.array(seen), bounds=np.array(ebd.shard_bounds(n, rank, world)))
     dist.destroy_process_group()
 
@@ -80,6 +87,10 @@ def test_two_rank_gloo_sharding_and_fanout(tmp_path):
     assert np.array_equal(r0["pw"], r1["pw"], equal_nan=True) and np.array_equal(r0["lagged"], r1["lagged"])
     assert not np.isnan(r0["pw"][np.triu_indices(5, 1)]).any() and not np.isnan(r0["lagged"]).any()
     assert len(r0["seen"]) + len(r1["seen"]) == 10 and len(r0["seen"]) == 5
+    # the column path (block upload per rank) gives the same bits as the general host path, on both ranks
+    for r in (r0, r1):
+        assert np.array_equal(r["pw_cols"], r0["pw"], equal_nan=True) and np.array_equal(r["lagged_cols"], r0["lagged"])
+        assert int(r["block_puts"]) >= 1
     # and equal to what one process computes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
 
