@@ -26,6 +26,9 @@
  *    tasks issued from different host threads run concurrently on one GPU.
  *  - thread safety: all entry points may be called concurrently; calls on the same (device, lane)
  *    serialise on that lane's stream and workspace.
+ *  - repeated eb2_ksg_mi_rows / eb2_ksg_mi calls with EB2_FLAG_DEVICE_INPUT and the same arguments are captured into a
+ *    CUDA graph on their third occurrence and replayed afterwards (results are bit-identical; the buffer is read
+ *    anew on every call).  Environment variable EB2_GRAPH=0 disables this.
  */
 #ifndef ENNEMI_B200_H
 #define ENNEMI_B200_H
