@@ -331,3 +331,23 @@ def test_block_upload_path(oracle_backend, monkeypatch):
         warnings.simplefilter("always")
         out_host = eb.pairwise_mi(const)
     assert eq(out_dev, out_host) and len(w_dev) == len(w_host) == 5
+
+
+def test_noise_stream_skip_keeps_the_draw_sequence():
+    """Skipping a draw (the caller already holds its values: memoised descriptors) must leave the stream exactly
+    where drawing it would have — the reference's noise depends only on the sequence of draw shapes
+    (``ennemi/_driver.py:874-899``)."""
+    from ennemi_b200 import _align
+    ref = np.random.default_rng(_align.NOISE_SEED)
+    a, b, c = (ref.normal(0.0, _align.NOISE_SCALE, sh) for sh in ((97,), (97,), (97, 3)))
+    s1 = _align._NoiseStream()
+    s1.skip((97,))
+    assert np.array_equal(s1.normal((97,)), b) and np.array_equal(s1.normal((97, 3)), c)
+    s2 = _align._NoiseStream()
+    assert np.array_equal(s2.normal((97,)), a)
+    s2.skip((97,))
+    assert np.array_equal(s2.normal((97, 3)), c)
+    _align._NoiseStream._cache.clear()                  # nothing memoised: the generator has to be replayed
+    s3 = _align._NoiseStream()
+    s3.skip((97,)); s3.skip((97,))
+    assert np.array_equal(s3.normal((97, 3)), c)
