@@ -85,6 +85,27 @@ def cpu_baseline_block(xs, ys, steps=1):
             "seconds_per_estimate": best}
 
 
+def cpu_pairwise_block(data, k=K_NEIGH, pairs_timed=2):
+    """The reference's CPU path for the pairwise_mi leg, on a bounded sample: `pairs_timed` of the 2,016 variable pairs
+    through the oracle's SciPy backend (= the reference's cKDTree calls on the preprocessed columns), scaled to the
+    whole matrix on one core and on all the box's cores (the reference fans pairs out over cpu_count threads,
+    ennemi/_driver.py:749)."""
+    import oracle
+    from ennemi_b200 import _align
+    secs = []
+    for j in range(1, pairs_timed + 1):
+        xs, ys, _ = _align.rescaled(data[:, 0].copy(), data[:, j].copy(), None, False, False)
+        t0 = time.perf_counter()
+        oracle.ksg_mi(xs, ys, k, backend="scipy")
+        secs.append(time.perf_counter() - t0)
+    per_pair = min(secs)
+    n_pairs = data.shape[1] * (data.shape[1] - 1) // 2
+    cores = os.cpu_count() or 1
+    return {"kind": "port", "seconds_per_pair": per_pair, "pairs_timed": pairs_timed, "cores": cores,
+            "estimated_total_s_one_core": per_pair * n_pairs, "estimated_total_s_all_cores": per_pair * n_pairs / cores,
+            "sample": f"{pairs_timed} of {n_pairs} pairs timed on one thread (SciPy cKDTree calls of the reference), scaled linearly"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,6 +328,8 @@ def run_gpu(args):
                             + (", tasks dealt over the ranks + one all_gather" if world > 1 else "")}
         ebd.enable_task_fanout(False)
         ebd.enable_row_sharding(True)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            pairwise["cpu_reference"] = cpu_pairwise_block(data)
 
     brute = None
     if world == 1 and not args.no_brute:
