@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import itertools
 import threading
-import time
 import warnings
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
@@ -57,42 +56,50 @@ def window_stats(view: np.ndarray) -> Tuple[float, float]:
 
 class NoiseBank:
     """The reference's fixed-seed noise draws (``_driver.py:874,883``), memoised on the host by
-    ``_align._NoiseStream`` and mirrored on each GPU under a cache key.  Least-recently-used entries are
-    dropped from the devices once more than ``MAX_ENTRIES`` draw sequences are live, but never while they
-    may still be referenced by a running task (entries used within the last ``MIN_AGE_S`` seconds stay)."""
+    ``_align._NoiseStream`` and mirrored on each GPU under a cache key.  Every :class:`ColumnStore` pins the
+    keys it was handed until it is closed (its memoised descriptors keep referring to them without coming back
+    here), so least-recently-used entries are dropped from the devices only once more than ``MAX_ENTRIES`` draw
+    sequences are live AND no running call holds them."""
 
     _lock = threading.Lock()
-    _keys: "OrderedDict[tuple, list]" = OrderedDict()       # draw-shape sequence -> [cache key, last use]
+    _keys: "OrderedDict[tuple, list]" = OrderedDict()       # draw-shape sequence -> [cache key, pin count]
     _on_device: Dict[int, set] = {}
     MAX_ENTRIES = 64
-    MIN_AGE_S = 120.0
 
     @classmethod
-    def key_for(cls, shapes: tuple, values: np.ndarray, dev: int) -> int:
+    def key_for(cls, shapes: tuple, values: np.ndarray, dev: int, store: "Optional[ColumnStore]" = None) -> int:
         ordinal = _devices.ordinal(dev)
-        now = time.monotonic()
         with cls._lock:
             entry = cls._keys.get(shapes)
             if entry is None:
-                entry = cls._keys[shapes] = [_new_key(), now]
-                while len(cls._keys) > cls.MAX_ENTRIES:
-                    oldest = next(iter(cls._keys))
-                    if now - cls._keys[oldest][1] < cls.MIN_AGE_S:
-                        break
-                    old = cls._keys.pop(oldest)[0]
-                    for d, have in cls._on_device.items():
-                        if old in have:
-                            have.discard(old)
-                            _native.cache_drop(old, dev=d)
+                entry = cls._keys[shapes] = [_new_key(), 0]
+                if len(cls._keys) > cls.MAX_ENTRIES:
+                    for old_shapes in [sh for sh, e in cls._keys.items() if e[1] == 0 and e is not entry]:
+                        if len(cls._keys) <= cls.MAX_ENTRIES:
+                            break
+                        old = cls._keys.pop(old_shapes)[0]
+                        for d, have in cls._on_device.items():
+                            if old in have:
+                                have.discard(old)
+                                _native.cache_drop(old, dev=d)
             else:
-                entry[1] = now
                 cls._keys.move_to_end(shapes)
             key = entry[0]
+            if store is not None and store._pin_noise(shapes):
+                entry[1] += 1
             have = cls._on_device.setdefault(ordinal, set())
             if key not in have:
                 _native.cache_put(key, np.ravel(values), dev=dev)
                 have.add(key)
             return key
+
+    @classmethod
+    def release(cls, shapes_list) -> None:
+        with cls._lock:
+            for shapes in shapes_list:
+                entry = cls._keys.get(shapes)
+                if entry is not None and entry[1] > 0:
+                    entry[1] -= 1
 
 
 class ColumnStore:
@@ -114,6 +121,8 @@ class ColumnStore:
         self._blocks: List[Tuple[np.ndarray, List[int]]] = []
         self._block_of: Dict[int, int] = {}
         self._descs: Dict[tuple, tuple] = {}
+        self._noise_pins: set = set()
+        self._inflight: Dict[tuple, threading.Event] = {}
         # whole-column mean/std of every block column computed right after the upload, in one call
         # (the windows of every pairwise_mi task; lagged windows are computed on demand)
         self.full_stats = full_stats
@@ -137,24 +146,52 @@ class ColumnStore:
             self._block_of[key] = len(self._blocks) - 1
         return keys
 
-    def ensure(self, dev: int, key: int) -> None:
+    def _pin_noise(self, shapes: tuple) -> bool:
+        """True the first time this store is handed the noise vector of ``shapes`` (NoiseBank then counts a pin)."""
         with self._lock:
-            have = self._on_device.setdefault(_devices.ordinal(dev), set())
-            if key in have:
-                return
-            bid = self._block_of.get(key)
+            if shapes in self._noise_pins:
+                return False
+            self._noise_pins.add(shapes)
+            return True
+
+    def ensure(self, dev: int, key: int) -> None:
+        """Uploads ``key`` (or the block it belongs to) to ``dev`` unless it is there already.  The store lock is
+        held only to decide who uploads: the copy itself runs unlocked (two lanes may upload different variables
+        side by side), and a second caller of the same variable waits for the first one's upload."""
+        ordinal = _devices.ordinal(dev)
+        bid = self._block_of.get(key)
+        unit = (ordinal, "b", bid) if bid is not None else (ordinal, "k", key)
+        while True:
+            with self._lock:
+                have = self._on_device.setdefault(ordinal, set())
+                if key in have:
+                    return
+                waiter = self._inflight.get(unit)
+                if waiter is None:
+                    mine = self._inflight[unit] = threading.Event()
+                    break
+            waiter.wait()
+        try:
+            stats = {}
             if bid is None:
                 _native.cache_put(key, self._cols[key], dev=dev)
-                have.add(key)
-                return
-            block, keys = self._blocks[bid]
-            _native.cache_put_block(keys, block, dev=dev)
-            have.update(keys)
-            n = block.shape[0]
-            if self.full_stats and n >= DEVICE_STATS_MIN_ROWS:
-                means, stds = _native.cache_stats_many(keys, [0] * len(keys), n, dev=dev)
-                for k, m, sd in zip(keys, means, stds):
-                    self._stats.setdefault((k, 0, n), (float(m), float(sd)))
+                done = [key]
+            else:
+                block, keys = self._blocks[bid]
+                _native.cache_put_block(keys, block, dev=dev)
+                done = keys
+                n = block.shape[0]
+                if self.full_stats and n >= DEVICE_STATS_MIN_ROWS:
+                    means, stds = _native.cache_stats_many(keys, [0] * len(keys), n, dev=dev)
+                    stats = {(k, 0, n): (float(m), float(sd)) for k, m, sd in zip(keys, means, stds)}
+            with self._lock:
+                self._on_device.setdefault(ordinal, set()).update(done)
+                for tag, value in stats.items():
+                    self._stats.setdefault(tag, value)
+        finally:
+            with self._lock:
+                self._inflight.pop(unit, None)
+            mine.set()
 
     def cached_desc(self, tag: tuple):
         return self._descs.get(tag)
@@ -187,6 +224,8 @@ class ColumnStore:
                     _native.cache_drop(key, dev=dev)
                 except Exception:
                     pass
+        NoiseBank.release(self._noise_pins)
+        self._noise_pins = set()
         self._on_device.clear()
         self._cols.clear()
         self._blocks.clear()
@@ -260,7 +299,7 @@ class ColsTask:
             if self.preprocess and in_call_stats and not self.store.has_stats(tag):
                 values = stream.normal((n,))
                 shapes = shapes + ((n,),)
-                return _native.ColDesc(key, off, 1, float("nan"), 1.0, NoiseBank.key_for(shapes, values, dev), 0, 1)
+                return _native.ColDesc(key, off, 1, float("nan"), 1.0, NoiseBank.key_for(shapes, values, dev, self.store), 0, 1)
             reusable = True
             if self.preprocess:
                 mean, std = self.store.stats(tag, stats_of(key, off, view))
@@ -271,7 +310,7 @@ class ColsTask:
                 elif std == std:                                    # NaN std (NaN input): reported by the device
                     values = stream.normal((n,))
                     shapes = shapes + ((n,),)
-                    nkey = NoiseBank.key_for(shapes, values, dev)
+                    nkey = NoiseBank.key_for(shapes, values, dev, self.store)
                 else:
                     std = 0.0
             desc = _native.ColDesc(key, off, 1, mean, std, nkey, 0, 1)
@@ -314,7 +353,7 @@ class ColsTask:
                 elif not np.any(np.isnan(zstd)):
                     values = stream.normal((n, c))
                     shapes = shapes + ((n, c),)
-                    nkey = NoiseBank.key_for(shapes, values, dev)
+                    nkey = NoiseBank.key_for(shapes, values, dev, self.store)
                 else:
                     zstd = None
             for j, (key, off) in enumerate(zip(self.zkeys, z_offs)):

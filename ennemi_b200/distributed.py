@@ -136,24 +136,36 @@ def fan_out(func: Callable, params: Sequence, callback: Optional[Callable[[int],
             group=None, runner: Optional[Callable] = None) -> List[float]:
     """Runs ``func(params[i])`` for the tasks ``i = rank, rank + world, ...`` on this rank and returns
     the full task-ordered result list on every rank (one all_gather of fp64 scalars).  ``runner(func,
-    params, callback)`` executes this rank's share (default: sequentially)."""
+    params, callback)`` executes this rank's share (default: sequentially).
+
+    Failures are agreed on before anybody raises: a rank whose share failed (a NaN column in one of its
+    pairs, ``k`` too large for one window, a CUDA error) still enters the collective with an error flag,
+    and every rank then raises — the failing rank its own exception, the others a copy of the first
+    failing rank's — so that a data-dependent error is never a multi-rank hang."""
     rank, size = world()
     mine = list(range(rank, len(params), size))
     slots = len(range(0, len(params), size)) if size else 0
-    local = np.full(slots, np.nan)
+    local = np.full(slots + 1, np.nan)          # last slot: 1.0 when this rank's share failed
 
     def local_cb(slot: int) -> None:
         if callback is not None:
             callback(mine[slot])
 
-    if runner is None:
-        values = []
-        for slot, i in enumerate(mine):
-            values.append(func(params[i]))
-            local_cb(slot)
-    else:
-        values = runner(func, [params[i] for i in mine], local_cb)
-    local[:len(mine)] = values
+    error: Optional[BaseException] = None
+    try:
+        if runner is None:
+            values = []
+            for slot, i in enumerate(mine):
+                values.append(func(params[i]))
+                local_cb(slot)
+        else:
+            values = runner(func, [params[i] for i in mine], local_cb)
+        local[:len(mine)] = values
+    except Exception as e:                       # noqa: BLE001 - re-raised below, after the ranks agreed
+        if size == 1:
+            raise
+        error = e
+    local[slots] = 0.0 if error is None else 1.0
     if size == 1:
         return [float(v) for v in local[:len(params)]]
     import torch
@@ -165,4 +177,15 @@ def fan_out(func: Callable, params: Sequence, callback: Optional[Callable[[int],
     gathered = [torch.empty_like(t) for _ in range(size)]
     dist.all_gather(gathered, t, group=group)
     table = np.stack([g.cpu().numpy() for g in gathered])          # [rank][slot]
+    failed = [r for r in range(size) if table[r, slots] != 0.0]
+    if failed:
+        # every rank reaches this point: exchange what went wrong, then raise everywhere
+        info = [None] * size
+        mine_info = None if error is None else (type(error).__name__, str(error))
+        dist.all_gather_object(info, mine_info, group=group)
+        if error is not None:
+            raise error
+        kind, message = info[failed[0]] or ("RuntimeError", "unknown failure")
+        exc = ValueError if kind == "ValueError" else RuntimeError
+        raise exc(f"{message} (raised as {kind} on rank {failed[0]})")
     return [float(table[i % size, i // size]) for i in range(len(params))]

@@ -68,9 +68,21 @@ def _worker(rank, world, port, out_dir):
     lagged_cols = eb.estimate_mi(x[:, 0], x[:, 1:3], lag=[0, 1, 2])
     api.DEVICE_COLUMNS_MIN_ROWS = 10 ** 9
     ebd.enable_task_fanout(False)
+    # a failure in ONE rank's share (task 3 runs on rank 1 only) must surface as the same exception type on
+    # every rank after the collective, not as a hang of the ranks that had nothing to complain about
+    def touchy(p):
+        if p == 3:
+            raise ValueError("input contains NaNs")
+        return float(p)
+    try:
+        ebd.fan_out(touchy, list(range(6)))
+        agreed = "no error"
+    except ValueError as e:
+        agreed = "ValueError:" + str(e)
+    clean = ebd.fan_out(float, list(range(6)))          # the group is still usable afterwards
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), sharded=sharded, want=full["value"], pw=pw, lagged=lagged,
              pw_cols=pw_cols, lagged_cols=lagged_cols, block_puts=getattr(fake, "block_puts", 0),
-             seen=np.array(seen), bounds=np.array(ebd.shard_bounds(n, rank, world)))
+             agreed=agreed, clean=np.array(clean), seen=np.array(seen), bounds=np.array(ebd.shard_bounds(n, rank, world)))
     dist.destroy_process_group()
 
 
@@ -91,8 +103,10 @@ def test_two_rank_gloo_sharding_and_fanout(tmp_path):
     for r in (r0, r1):
         assert np.array_equal(r["pw_cols"], r0["pw"], equal_nan=True) and np.array_equal(r["lagged_cols"], r0["lagged"])
         assert int(r["block_puts"]) >= 1
-    # and equal to what one process computes
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    # a one-rank failure is raised on both ranks (rank 1 its own exception, rank 0 a copy naming rank 1)
+    assert str(r1["agreed"]) == "ValueError:input contains NaNs"
+    assert str(r0["agreed"]).startswith("ValueError:input contains NaNs") and "rank 1" in str(r0["agreed"])
+    assert np.array_equal(r0["clean"], np.arange(6.0)) and np.array_equal(r1["clean"], np.arange(6.0))
 
 
 def test_single_process_reference_for_fanout(oracle_backend, tmp_path):

@@ -263,3 +263,51 @@ def test_graph_replay_matches_eager(monkeypatch):
     torch.cuda.synchronize()
     with pytest.raises(ValueError, match="data must be finite"):
         call()
+
+
+def test_pairwise_full_size_vs_reference_calls():
+    """BASELINE.json configs[3] at full size through the public API: pairwise_mi on (100000, 64) — the block upload,
+    device statistics, prepared-variable cache and batched pair path the bench's pairwise number comes from — against
+    the reference's own SciPy calls (oracle "scipy" backend) on the columns prepared as the reference prepares them
+    (ennemi/_driver.py:703-707, 871-902).  18 sampled pairs within 1e-10; eps / n_x / n_y of two pairs bit for bit."""
+    import oracle
+    from ennemi_b200 import _align, _native as nat
+    rng = np.random.default_rng(0)
+    mix = np.eye(64) + 0.15 * rng.normal(size=(64, 64))
+    data = rng.normal(size=(100_000, 64)) @ mix
+    got = eb.pairwise_mi(data, k=3)
+    assert got.shape == (64, 64) and np.all(np.isnan(np.diag(got))) and np.array_equal(got, got.T, equal_nan=True)
+    pairs = [(0, 1), (0, 63), (62, 63), (31, 32)] + [tuple(sorted(rng.choice(64, 2, replace=False))) for _ in range(14)]
+    for t, (i, j) in enumerate(pairs):
+        xs, ys, _ = _align.rescaled(data[:, i].copy(), data[:, j].copy(), None, False, False)
+        want = oracle.ksg_mi(xs, ys, 3, backend="scipy")
+        assert abs(got[i, j] - want["value"]) <= TOL, (i, j, got[i, j], want["value"])
+        if t < 2:
+            value, parts = nat.ksg_mi(nat.pack_coords([xs, ys]), 3, details=True)
+            assert np.array_equal(parts["eps"], want["eps"])
+            assert np.array_equal(parts["nx"], want["nx"]) and np.array_equal(parts["ny"], want["ny"])
+            assert abs(value - got[i, j]) <= 1e-13
+
+
+def test_cmi_lag_sweep_full_size_vs_reference_calls():
+    """BASELINE.json configs[2] at full size through the public API: estimate_mi(y, x, lag=range(50), cond=z) at
+    N = 200,000 with a 3-D condition (ennemi/_driver.py:477-483); three sampled lags against the reference's SciPy
+    calls on host-prepared windows (oracle.conditional_mi), eps and all three counts of one lag bit for bit."""
+    import oracle
+    from ennemi_b200 import _align, _native as nat
+    rng = np.random.default_rng(0)
+    n = 200_000
+    z = rng.normal(size=(n, 3)); x = rng.normal(size=n) + z[:, 0]; y = 0.5 * x + z[:, 1] + rng.normal(size=n)
+    lags = np.arange(50)
+    got = eb.estimate_mi(y, x, lag=lags, k=3, cond=z)
+    assert got.shape == (50, 1)
+    for t, lag in enumerate((0, 17, 49)):
+        task = _align.MiTask(x, y, lag, 49, 0, 3, None, z, np.zeros(3, dtype=int), False, False, True, False)
+        xs, ys, zs = _align.prepare(task)
+        want = oracle.conditional_mi(xs, ys, zs, 3, backend="scipy")
+        assert abs(got[lag, 0] - want["value"]) <= TOL, (lag, got[lag, 0], want["value"])
+        if t == 1:
+            value, parts = nat.cmi(nat.pack_coords([xs, ys, zs]), 3, details=True)
+            for key in ("eps", "nxz", "nyz", "nz"):
+                assert np.array_equal(parts[key], want[key]), key
+            assert abs(value - got[lag, 0]) <= 1e-13

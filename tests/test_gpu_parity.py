@@ -195,6 +195,23 @@ def test_full_size_properties_config2():
     assert nat.ksg_mi(coords, 3) == v_fast                                      # bitwise repeatable
 
 
+def test_full_size_config2_every_row_vs_reference_calls():
+    """BASELINE.json configs[1] (N = 10^6, k = 3): EVERY eps / n_x / n_y against the reference's own SciPy
+    calls (oracle "scipy" backend = cKDTree.query + query_ball_point on all rows,
+    /root/reference/ennemi/_entropy_estimators.py:100-110), bit for bit; value within 1e-10."""
+    import oracle
+    n = 1_000_000
+    rng = np.random.default_rng(0)
+    d = rng.multivariate_normal([0, 0], [[1, 0.6], [0.6, 1]], size=n)
+    x, y = np.ascontiguousarray(d[:, 0]), np.ascontiguousarray(d[:, 1])
+    want = oracle.ksg_mi(x, y, 3, backend="scipy")
+    value, parts = nat.ksg_mi(nat.pack_coords([x, y]), 3, details=True)
+    assert int(np.count_nonzero(parts["eps"] != want["eps"])) == 0
+    assert int(np.count_nonzero(parts["nx"] != want["nx"])) == 0
+    assert int(np.count_nonzero(parts["ny"] != want["ny"])) == 0
+    assert close(value, want["value"])
+
+
 def test_full_size_other_configs():
     """configs[2] one lag (N=200,000, 3-D condition), configs[4] Ross (N=500,000, 16 classes, k=5)
     and 4-D entropy (N=500,000, k=5) against the SciPy backend = the reference's own calls."""
