@@ -47,6 +47,9 @@ SAMPLE_STRIDE = 50             # CPU baseline: every 50th row is queried, trees 
 # dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel<2,4> at this workload, one ncu --set full capture
 # (profiles/ncu_r01_summary.md): the 16 MB point set is read once, everything else stays in the 126 MB L2
 NCU_DRAM_BYTES_PER_LAUNCH = 16.7e6
+# the workload both arms (`--impl ours` / `--impl reference`) run: identical `config` on both JSON lines
+CONFIG = {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]); a step = one "
+                      "complete estimate per GPU", "n": N_ROWS, "k": K_NEIGH, "rho": RHO, "seed": 0}
 
 
 def make_data(n=N_ROWS, seed=0):
@@ -107,25 +110,29 @@ def cpu_pairwise_block(data, k=K_NEIGH, pairs_timed=2):
 
 
 def run_reference(args):
+    """The reference's CPU path, MEASURED: every step is one complete estimate (three cKDTrees on all 10^6 rows, the
+    k-NN query and both ball counts for EVERY row — stride 1, nothing extrapolated), one thread, as the reference
+    runs a single estimate.  ~9 s per step on the GPU box's host: `--steps 25` is ~4 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     y, x = make_data()
     xs, ys = preprocessed(y, x)
-    for _ in range(args.warmup):
-        cpu_step(xs, ys)
-    secs = [cpu_step(xs, ys) for _ in range(args.steps)]
+    for _ in range(min(args.warmup, 1)):          # one warm-up estimate is enough for a CPU path (page-in, allocator)
+        cpu_step(xs, ys, stride=1)
+    secs = [cpu_step(xs, ys, stride=1) for _ in range(args.steps)]
     per = sum(secs) / len(secs)
     value = 1.0 / per
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1])",
-                   "n": N_ROWS, "k": K_NEIGH},
+        "config": dict(CONFIG),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"oracle SciPy backend (the reference's cKDTree calls): trees on all rows, queries for "
-                                   f"every {SAMPLE_STRIDE}th row scaled x{SAMPLE_STRIDE}; single estimate = 1 thread in the reference"},
+                         "sample": "oracle SciPy backend = the reference's own cKDTree calls (_entropy_estimators.py:100-110) on ALL "
+                                   f"{N_ROWS:,} rows per step (no sub-sampling, no scaling); a single estimate is one thread in the "
+                                   f"reference (benchmarks/bench_large_sample_mi.py:6-7); warm-up steps run: {min(args.warmup, 1)}; "
+                                   f"host has {os.cpu_count()} cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -352,12 +359,12 @@ def run_gpu(args):
         "metric": METRIC, "value": units * 1e3 / per_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]); a step = one "
-                               "estimate per GPU (N > 1: independent same-shape batches fanned out, no collective; the "
-                               "row-sharded single estimate is in `sharded`)",
-                   "n": N_ROWS, "k": K_NEIGH, "algorithm": "exact two-level search, per-lane window walk inside staged chunks (bit-exact eps and counts); brute force in brute_force",
-                   "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
-                   "parallelism": "single GPU" if world == 1 else f"task fan-out x{world} (+ rows/{world} in `sharded`)"},
+        "config": dict(CONFIG),
+        "details": {"step": "N > 1: independent same-shape batches fanned out, one estimate per GPU per step, no collective; the "
+                            "row-sharded single estimate is in `sharded`",
+                    "algorithm": "exact two-level search (bit-exact eps and counts); brute force in brute_force",
+                    "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
+                    "parallelism": "single GPU" if world == 1 else f"task fan-out x{world} (+ rows/{world} in `sharded`)"},
         "mi": last["value"] if world == 1 else last["value_own"],
         "e2e": {"value": units * 1e3 / (ms_e2e / args.steps), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(coords_host.nbytes), "d2h_bytes_per_step": 44,

@@ -412,6 +412,59 @@ def _helper_pool():
         return _pool
 
 
+def _check_status(status) -> None:
+    for st in status:
+        if st:
+            code, data_flags = int(st) & 0xFF, int(st) >> 8
+            if code == _native.ERR_NONFINITE:
+                if data_flags & 1:
+                    raise ValueError(_checks.MSG_NANS_LEFT)
+                raise ValueError("data must be finite, check for nan or inf values")
+            raise RuntimeError(f"ennemi_b200: batched estimate failed with code {code}")
+
+
+def run_pairs(tasks: List["ColsTask"]) -> List[float]:
+    """All unconditional column tasks of one window length in ONE library call (``eb2_ksg_mi_pairs``): every distinct
+    (variable, role) descriptor is rescaled and sorted once on the device, the pairs share them."""
+    dev = _devices.current()
+    out: List[float] = []
+    index: Dict[int, int] = {}
+    cols: List[_native.ColDesc] = []
+    pairs: List[Tuple[int, int]] = []
+    n = None
+
+    def flush() -> None:
+        nonlocal index, cols, pairs
+        if pairs:
+            values, status = _native.ksg_mi_pairs(cols, np.asarray(pairs, dtype=np.int32), n, tasks[0].k, dev=dev)
+            _check_status(status)
+            out.extend(float(v) for v in values)
+        index, cols, pairs = {}, [], []
+
+    for task in tasks:
+        descs, n_t = task.describe(dev)
+        if n is not None and n_t != n:
+            flush()                                  # (windows of another length: a call of their own)
+        n = n_t
+        # the prepared variables of one call stay on the device together: bound them (~40 bytes per row each)
+        if len(cols) + 2 > max(2, PAIR_CALL_BYTES // (40 * max(n, 1))):
+            flush()
+        ids = []
+        for d in descs:
+            # memoised descriptors are the same object for every task that uses a variable in a role
+            ident = index.get(id(d))
+            if ident is None:
+                ident = index[id(d)] = len(cols)
+                cols.append(d)
+            ids.append(ident)
+        pairs.append((ids[0], ids[1]))
+    flush()
+    return out
+
+
+PAIR_CALL_BYTES = 8 << 30     # device memory the prepared variables of one eb2_ksg_mi_pairs call may take
+
+
 BATCH = 8     # tasks per native call: one interpreter round trip (and one GIL release) per batch
 
 
@@ -421,12 +474,5 @@ def run_batch(tasks: List["ColsTask"]) -> List[float]:
     described = [t.describe(dev) for t in tasks]
     n = described[0][1]
     values, status = _native.mi_cols_batch([d for d, _ in described], n, tasks[0].k, dev=dev)
-    for st in status:
-        if st:
-            code, data_flags = int(st) & 0xFF, int(st) >> 8
-            if code == _native.ERR_NONFINITE:
-                if data_flags & 1:
-                    raise ValueError(_checks.MSG_NANS_LEFT)
-                raise ValueError("data must be finite, check for nan or inf values")
-            raise RuntimeError(f"ennemi_b200: batched estimate failed with code {code}")
+    _check_status(status)
     return [float(v) for v in values]

@@ -35,7 +35,7 @@ EXPORTS = (
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
-    "eb2_cache_put_block", "eb2_cache_stats_many",
+    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs",
 )
 
 _lib = None
@@ -99,6 +99,7 @@ def load():
         lib.eb2_cmi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _i64, _i64, _c_dp]
         lib.eb2_cache_stats.argtypes = [_int, ctypes.c_uint64, _i64, _i64, _i64, _c_dp, _c_dp]
         lib.eb2_mi_cols_batch.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _i64, _int, _u32, _c_dp, ctypes.POINTER(_int)]
+        lib.eb2_ksg_mi_pairs.argtypes = [_int, ctypes.POINTER(ColDesc), _int, _vp, _i64, _i64, _int, _u32, _c_dp, ctypes.POINTER(_int)]
         for name in EXPORTS:
             getattr(lib, name)
         _lib = lib
@@ -426,6 +427,21 @@ def mi_cols_batch(tasks, n: int, k: int, dev: int = 0, flags: int = 0):
     if rc:
         _raise(rc)
     return values, np.frombuffer(status, dtype=np.int32).copy()
+
+
+def ksg_mi_pairs(cols, pairs: np.ndarray, n: int, k: int, dev: int = 0, flags: int = 0):
+    """Every pair ``(cols[pairs[t, 0]], cols[pairs[t, 1]])`` of the prepared variables ``cols`` (descriptors) in one
+    call (``eb2_ksg_mi_pairs``).  Returns (values, status) arrays as :func:`mi_cols_batch` does."""
+    lib = load()
+    arr = (ColDesc * len(cols))(*cols)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    values = np.empty(len(pairs))
+    status = (ctypes.c_int * max(len(pairs), 1))()
+    rc = lib.eb2_ksg_mi_pairs(dev, arr, len(cols), pairs.ctypes.data, len(pairs), n, k, flags,
+                              values.ctypes.data_as(_c_dp), status)
+    if rc:
+        _raise(rc)
+    return values, np.frombuffer(status, dtype=np.int32)[:len(pairs)].copy()
 
 
 def mi_cols_rows(cols, n: int, k: int, row_lo: int, row_hi: int, dev: int = 0, flags: int = 0) -> np.ndarray:

@@ -85,6 +85,8 @@ def _run_column_batches(tasks, max_threads: Optional[int], time_estimate: float,
     rotate over the (GPU, lane) workers, one native call per batch."""
     from . import _columns
     devices = _devices.visible()
+    if all(not t.zkeys for t in tasks):
+        return _run_pair_calls(tasks, devices, max_threads, callback)
     workers = max(1, len(devices)) * WORKERS_PER_DEVICE
     if len(tasks) * time_estimate < INLINE_BUDGET_S:
         workers = 1
@@ -109,6 +111,35 @@ def _run_column_batches(tasks, max_threads: Optional[int], time_estimate: float,
     with concurrent.futures.ThreadPoolExecutor(workers, "ennemi-b200-work") as pool:
         futures = [pool.submit(work, b, _devices.with_lane(devices[b % len(devices)], (b // len(devices)) % _devices.LANES))
                    for b in range(len(batches))]
+        concurrent.futures.wait(futures)
+        for f in futures:
+            f.result()
+    return results
+
+
+def _run_pair_calls(tasks, devices, max_threads: Optional[int], callback: Callable[[int], None]) -> List[float]:
+    """Unconditional column tasks: each GPU takes one contiguous share of the task list and estimates it with ONE
+    library call (``eb2_ksg_mi_pairs``: every variable rescaled and sorted once, all pairs batched per stage)."""
+    from . import _columns
+    parts = max(1, min(len(devices), len(tasks)))
+    if max_threads is not None:
+        parts = max(1, min(parts, max_threads))
+    bounds = [(len(tasks) * p) // parts for p in range(parts + 1)]
+    results: List[float] = [float("nan")] * len(tasks)
+
+    def work(p: int, dev: int) -> None:
+        lo, hi = bounds[p], bounds[p + 1]
+        with _devices.use(dev):
+            values = _columns.run_pairs(tasks[lo:hi])
+        for i, v in zip(range(lo, hi), values):
+            results[i] = v
+            callback(i)
+
+    if parts == 1:
+        work(0, devices[0] if devices else _devices.current())
+        return results
+    with concurrent.futures.ThreadPoolExecutor(parts, "ennemi-b200-work") as pool:
+        futures = [pool.submit(work, p, devices[p]) for p in range(parts)]
         concurrent.futures.wait(futures)
         for f in futures:
             f.result()

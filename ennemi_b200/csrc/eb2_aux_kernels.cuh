@@ -270,6 +270,8 @@ struct PrepCol {
   const double* noise;     // NULL: no noise
   long long noff, nstride;
   const double* dstats;    // non-NULL (EB2_FLAG_DEVICE_STATS): mean = dstats[1], std = dstats[3], computed in this call
+  int* flag;               // non-NULL: this column's own flag word (instead of PrepArgs::flags)
+  double* dst;             // non-NULL: this column's own destination (instead of raw + t * n)
 };
 struct PrepArgs {
   PrepCol col[kMaxDimAny];
@@ -286,13 +288,14 @@ __global__ void prep_kernel(const PrepArgs a) {
   const long long i = idx - (long long)t * a.n;
   const PrepCol& c = a.col[t];
   double v = c.src[c.off + i * c.stride];
-  if (v != v) atomicOr(a.flags, 1);
+  int* flags = c.flag ? c.flag : a.flags;
+  if (v != v) atomicOr(flags, 1);
   double mean = c.mean, std = c.std;
   if (c.dstats && std != 0.0) {
     mean = c.dstats[1];
     std = c.dstats[3];
     if (fabs(std) < 1e-20) {       // ennemi/_driver.py:879: the caller has to take the warning path
-      if (i == 0) atomicOr(a.flags, 8);
+      if (i == 0) atomicOr(flags, 8);
       std = 0.0;
     }
   }
@@ -300,7 +303,7 @@ __global__ void prep_kernel(const PrepArgs a) {
     v = __ddiv_rn(__dsub_rn(v, mean), std);
     if (c.noise) v = __dadd_rn(v, c.noise[c.noff + i * c.nstride]);
   }
-  a.raw[idx] = v;
+  if (c.dst) c.dst[i] = v; else a.raw[idx] = v;
 }
 
 // ---- NumPy-exact mean / standard deviation of a cached column window ------------------------------

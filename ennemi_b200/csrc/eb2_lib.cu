@@ -35,6 +35,7 @@
 #include "../../include/ennemi_b200.h"
 #include "eb2_aux_kernels.cuh"
 #include "eb2_launch.h"
+#include "eb2_ksg2.h"
 
 namespace {
 
@@ -64,6 +65,7 @@ struct CudaFail {
     if (e_ != cudaSuccess) throw CudaFail{e_, #x, __LINE__}; \
   } while (0)
 
+constexpr int EB2_ERR_RETRY_GENERAL = 1000;   // internal code, never returned through the C ABI
 constexpr int kMaxDev = 64;
 constexpr int kMaxLanes = 4;       // independent streams ("lanes") per device: `dev` = ordinal | lane << 8
 constexpr int kNumEvents = 8;
@@ -157,6 +159,7 @@ Ctx& get_ctx(int dev_lane) {
   CU(cudaDeviceGetDefaultMemPool(&pool, dev));
   uint64_t keep = std::numeric_limits<uint64_t>::max();   // keep freed workspace cached in the pool
   CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (lane == 0) CU(k2::init());
   if (lane == 0) {
     // reserve workspace once: the pool keeps it (release threshold above), so the first large call does not
     // pay for growing the pool allocation by allocation
@@ -698,6 +701,17 @@ void run_search(Scratch& s, const double* qcoord, const double* radius, const do
   s.launches++;
 }
 
+constexpr int kPsiTab = 1 << 16;
+// psi_ref(n) for n < kPsiTab, filled once per lane by the same device function an evaluation would use
+void ensure_psi_tab(Scratch& s) {
+  if (s.c.psi_tab) return;
+  void* p = nullptr;
+  CU(cudaMallocAsync(&p, sizeof(double) * kPsiTab, s.c.stream));       // kept until eb2_shutdown
+  s.c.psi_tab = static_cast<double*>(p);
+  psi_table_kernel<<<cdiv(kPsiTab, 256), 256, 0, s.c.stream>>>(s.c.psi_tab, kPsiTab);
+  s.launches++;
+}
+
 // per-tile digamma partials -> 4 doubles on the device
 double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* cc, const double* dist, const TileSet& ts) {
   double* out4 = s.result;              // zeroed by begin_call
@@ -708,14 +722,7 @@ double* run_psi(Scratch& s, int mode, const int* ca, const int* cb, const int* c
   if (!ts.count) return out4;
   PsiArgs a;
   a.cnt_a = ca; a.cnt_b = cb; a.cnt_c = cc; a.dist = dist; a.tiles = ts.dev; a.ntiles = ts.count; a.mode = mode;
-  constexpr int kPsiTab = 1 << 16;
-  if (!s.c.psi_tab && mode != LOG_DIST) {
-    void* p = nullptr;
-    CU(cudaMallocAsync(&p, sizeof(double) * kPsiTab, s.c.stream));       // kept until eb2_shutdown
-    s.c.psi_tab = static_cast<double*>(p);
-    psi_table_kernel<<<cdiv(kPsiTab, 256), 256, 0, s.c.stream>>>(s.c.psi_tab, kPsiTab);
-    s.launches++;
-  }
+  if (mode != LOG_DIST) ensure_psi_tab(s);
   a.tab = s.c.psi_tab; a.tab_n = s.c.psi_tab ? kPsiTab : 0;
   a.partial = s.dev<double>(static_cast<size_t>(ts.count) * 4);
   psi_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(a);
@@ -824,7 +831,7 @@ struct Input {
   uint32_t flags = 0;
 };
 
-const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* nonfinite_flag) {
+const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* nonfinite_flag, bool check_finite = true) {
   const double* raw = in.coords;
   const int64_t total = static_cast<int64_t>(d) * n;
   if (in.cols) {
@@ -842,7 +849,7 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
         throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
       PrepCol& pc = pa.col[t];
       pc.src = it->second.first; pc.off = c.off; pc.stride = c.stride; pc.mean = c.mean; pc.std = c.std;
-      pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride; pc.dstats = nullptr;
+      pc.noise = nullptr; pc.noff = c.noff; pc.nstride = c.nstride; pc.dstats = nullptr; pc.flag = nullptr; pc.dst = nullptr;
       if (c.nkey != 0) {
         auto nt = cache.find(c.nkey);
         if (nt == cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
@@ -869,8 +876,10 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
     CU(cudaMemcpyAsync(dv, in.coords, sizeof(double) * total, cudaMemcpyHostToDevice, s.c.stream));
     raw = dv;
   }
-  nonfinite_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(raw, total, nonfinite_flag);
-  s.launches++;
+  if (check_finite) {
+    nonfinite_kernel<<<cdiv(total, 256), 256, 0, s.c.stream>>>(raw, total, nonfinite_flag);
+    s.launches++;
+  }
   return raw;
 }
 
@@ -901,7 +910,7 @@ Derived* get_derived(Scratch& s, const eb2_col_t& col, int64_t n) {
     pa.d = 1; pa.n = n;
     PrepCol& pc = pa.col[0];
     pc.src = src->second.first; pc.off = col.off; pc.stride = col.stride; pc.mean = col.mean; pc.std = col.std;
-    pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride; pc.dstats = nullptr;
+    pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride; pc.dstats = nullptr; pc.flag = nullptr; pc.dst = nullptr;
     if (col.nkey != 0) {
       auto nt = sh.cache.find(col.nkey);
       if (nt == sh.cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
@@ -985,11 +994,14 @@ void export_outputs(Scratch& s, const PointSet& ps, const double* eps, const int
 // gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
 thread_local bool g_skip_timing = false;   // set by batched calls for all but their last task
 
-struct Res { double v[4]; unsigned long long pairs; int nonfinite; };
-static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40, "Res mirrors the device result block");
+struct Res { double v[4]; unsigned long long pairs; int nonfinite; int pad; unsigned long long rows; };
+static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40 && offsetof(Res, rows) == 48 && sizeof(Res) == 56,
+              "Res mirrors the device result block");
 
 // the synchronised result block -> error code / partial block
 int parse_result(const Res* h, int64_t rows, double* partial) {
+  if (rows < 0) rows = static_cast<int64_t>(h->rows);      // the bivariate pipeline counts the rows it reduced on the device
+  if (h->nonfinite & k2::kFlagOverflow) return EB2_ERR_RETRY_GENERAL;     // internal: the caller repeats on the general path
   if (h->nonfinite & 8) {
     g_data_flags = h->nonfinite;
     return fail(EB2_ERR_CONSTANT, "a window with device-computed statistics is constant (std < 1e-20): "
@@ -1033,7 +1045,7 @@ int finish_call(Scratch& s, const double* out4, const unsigned long long* pairs,
   Ctx& c = s.c;
   Res* h = s.host<Res>(1);
   if (out4 == s.result && s.result) {
-    CU(cudaMemcpyAsync(h, s.result, 44, cudaMemcpyDeviceToHost, c.stream));     // the whole block in one copy
+    CU(cudaMemcpyAsync(h, s.result, sizeof(Res), cudaMemcpyDeviceToHost, c.stream));     // the whole block in one copy
   } else {
     CU(cudaMemcpyAsync(h->v, out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, c.stream));
     CU(cudaMemcpyAsync(&h->pairs, pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
@@ -1440,18 +1452,77 @@ int64_t partition_min_rows() {
   return 300000;
 }
 
+// ---- the bivariate pipeline (eb2_ksg2.h) for ONE estimate --------------------------------------------------------
+// descriptors travel as kernel parameters (not through a staging copy) so that a captured graph carries them
+__global__ void k2_setup_kernel(const k2::Col c0, const k2::Col c1, const k2::Prob p, k2::Col* cols, k2::Prob* probs) {
+  cols[0] = c0;
+  cols[1] = c1;
+  probs[0] = p;
+  *c0.flag = 0;
+  *c1.flag = 0;
+}
+
+int64_t k2_min_rows() {
+  if (const char* e = getenv("EB2_K2_MIN")) return atoll(e);     // tuning / test knob
+  return 2048;
+}
+
+// raw = [x ; y] on the device.  Everything up to the result copy is enqueued on the lane's stream.
+double* run_k2(Scratch& s, const k2::Plan& plan, const double* raw, int64_t n, int k, int64_t row_lo, int64_t row_hi,
+               double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+  Ctx& c = s.c;
+  cudaStream_t st = c.stream;
+  const int k1t = (k + 1 <= 4) ? 4 : 8;
+  ensure_psi_tab(s);
+  k2::Col hc0 = k2::carve_col(s.dev<char>(k2::col_bytes(n)), n, raw);
+  k2::Col hc1 = k2::carve_col(s.dev<char>(k2::col_bytes(n)), n, raw + n);
+  k2::Prob hp = k2::carve_prob(s.dev<char>(k2::prob_bytes(plan, k1t)), plan, k1t, 0, 1);
+  hp.out = s.result;
+  if (eps_out) { hp.eps_row = s.dev<double>(n); CU(cudaMemsetAsync(hp.eps_row, 0xFF, sizeof(double) * n, st)); }
+  if (nx_out) { hp.nx_row = s.dev<long long>(n); CU(cudaMemsetAsync(hp.nx_row, 0xFF, sizeof(long long) * n, st)); }
+  if (ny_out) { hp.ny_row = s.dev<long long>(n); CU(cudaMemsetAsync(hp.ny_row, 0xFF, sizeof(long long) * n, st)); }
+  k2::Col* dcols = s.dev<k2::Col>(2);
+  k2::Prob* dprob = s.dev<k2::Prob>(1);
+  k2_setup_kernel<<<1, 1, 0, st>>>(hc0, hc1, hp, dcols, dprob);
+  s.launches++;
+  CU(cudaMemsetAsync(hp.partial, 0, sizeof(double) * 4 * plan.nblk, st));     // blocks of other shards read as zero
+  const k2::Shard sh{row_lo, row_hi, n};
+  CU(k2::colsort(dcols, 2, plan, st, &s.launches));
+  CU(k2::layout(dcols, dprob, 1, plan, st, &s.launches));
+  mark(s, 1);
+  CU(k2::knn(dcols, dprob, 1, plan, k, sh, c.sm_count, st, &s.launches));
+  mark(s, 2);
+  CU(k2::count_psi(dcols, dprob, 1, plan, sh, c.psi_tab, kPsiTab, st, &s.launches));
+  mark(s, 3);
+  CU(k2::finalize(dcols, dprob, 1, plan, st, &s.launches));
+  mark(s, 4);
+  if (eps_out) CU(cudaMemcpyAsync(eps_out, hp.eps_row, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (nx_out) CU(cudaMemcpyAsync(nx_out, hp.nx_row, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+  if (ny_out) CU(cudaMemcpyAsync(ny_out, hp.ny_row, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+  return s.result;
+}
+
 // ---- a1: KSG ------------------------------------------------------------------------------------
-static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
-                         double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+static int ksg_rows_once(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out, bool general_only) {
   const uint32_t flags = in.flags;
   return guarded(dev, [&](Ctx& c) {
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    // the bivariate pipeline (sample-sorted columns, bucket layout, one warp per 32 queries) takes every pruned estimate
+    // of a size it is built for; a bucket that outgrows its CTA (heavily tied data) sends the call back here with
+    // general_only set
+    bool plan_ok = false;
+    const k2::Plan plan = k2::make_plan(n, &plan_ok);
+    const bool use_k2 = plan_ok && !general_only && prune && !(flags & EB2_FLAG_BRUTE_COUNT) && k + 1 <= 8 &&
+                        n >= k2_min_rows() && !getenv("EB2_NO_K2");
     // Repeated resident estimates of one shape (unless EB2_GRAPH=0): the second call runs eagerly once the lane workspace has
     // its final size, the third is captured into a CUDA graph, later ones replay it with one launch.
     const bool graphable = graph_enabled() && !in.cols && (flags & EB2_FLAG_DEVICE_INPUT) && prune &&
-                           !(flags & EB2_FLAG_BRUTE_COUNT) && n >= partition_min_rows() && !getenv("EB2_NO_CELLS") &&
-                           !getenv("EB2_CELL_SORT") && !eps_out && !nx_out && !ny_out && partial && !g_skip_timing;
-    const int64_t gkey[8] = {static_cast<int64_t>(reinterpret_cast<intptr_t>(in.coords)), n, k, static_cast<int64_t>(flags), row_lo, row_hi,
+                           !(flags & EB2_FLAG_BRUTE_COUNT) &&
+                           (use_k2 || (n >= partition_min_rows() && !getenv("EB2_NO_CELLS") && !getenv("EB2_CELL_SORT"))) &&
+                           !eps_out && !nx_out && !ny_out && partial && !g_skip_timing;
+    const int64_t gkey[8] = {static_cast<int64_t>(reinterpret_cast<intptr_t>(in.coords)), n, k,
+                             static_cast<int64_t>(flags) | (use_k2 ? int64_t(1) << 40 : 0), row_lo, row_hi,
                              static_cast<int64_t>(reinterpret_cast<intptr_t>(c.arena)), static_cast<int64_t>(c.arena_cap)};
     if (graphable) {
       Ctx::GraphEntry* ge = graph_entry(c, gkey);
@@ -1466,6 +1537,14 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
     }
     CallInit ci = begin_call(s);
     const double* raw = nullptr;
+    if (use_k2) {
+      raw = stage_input(s, in, 2, n, ci.nonfinite, false);        // (the bucket count kernel checks for non-finite values)
+      double* out4 = run_k2(s, plan, raw, n, k, row_lo, row_hi, eps_out, nx_out, ny_out);
+      const int rc = finish_call(s, out4, ci.pairs, ci.nonfinite, -1, partial);
+      if (graphable && !capture && rc == EB2_OK && s.overflow == 0 && reinterpret_cast<intptr_t>(c.arena) == static_cast<intptr_t>(gkey[6]))
+        graph_entry(c, gkey)->seen = true;
+      return rc;
+    }
     const Derived* dx = nullptr;
     const Derived* dy = nullptr;
     const double* ys_direct = nullptr;
@@ -1571,6 +1650,13 @@ static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row
   });
 }
 
+static int ksg_rows_impl(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
+  const int rc = ksg_rows_once(dev, in, n, k, row_lo, row_hi, partial, eps_out, nx_out, ny_out, false);
+  if (rc != EB2_ERR_RETRY_GENERAL) return rc;
+  return ksg_rows_once(dev, in, n, k, row_lo, row_hi, partial, eps_out, nx_out, ny_out, true);
+}
+
 int eb2_ksg_mi_rows(int dev, const double* coords, int64_t n, int k, uint32_t flags, int64_t row_lo, int64_t row_hi,
                     double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out) {
   if (int rc0 = check_common(coords, n, 2, k)) return rc0;
@@ -1610,6 +1696,141 @@ int eb2_ksg_mi(int dev, const double* coords, int64_t n, int k, uint32_t flags, 
   const int rc = eb2_ksg_mi_rows(dev, coords, n, k, flags, 0, n, partial, eps_out, nx_out, ny_out);
   if (rc) return rc;
   return eb2_ksg_mi_finish(partial, n, k, value);
+}
+
+
+// ---- a7 for pairwise_mi: all pairs of a set of prepared variables in one call -------------------------------------
+// (the reference builds the same task list at ennemi/_driver.py:703-707 and maps it over a thread pool, :736-785).
+// Every variable is rescaled and sample-sorted ONCE; the pairs then go through the bivariate pipeline in batches,
+// each stage one launch for the whole batch (blockIdx.y / .z = pair).
+int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pairs, int64_t npairs, int64_t n, int k,
+                     uint32_t flags, double* values, int* status) {
+  if (!cols || !pairs || !values || !status || nvar < 1 || npairs < 0) return fail(EB2_ERR_ARG, "eb2_ksg_mi_pairs: bad argument");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, 2, k)) return rc0;
+  for (int64_t t = 0; t < 2 * npairs; ++t)
+    if (pairs[t] < 0 || pairs[t] >= nvar) return fail(EB2_ERR_ARG, "eb2_ksg_mi_pairs: variable index out of range");
+  bool plan_ok = false;
+  const k2::Plan plan = k2::make_plan(n, &plan_ok);
+  auto one_by_one = [&](int64_t t, bool general_only) {
+    const eb2_col_t two[2] = {cols[pairs[2 * t]], cols[pairs[2 * t + 1]]};
+    Input in; in.cols = two; in.flags = (flags & ~EB2_FLAG_DEVICE_INPUT) | EB2_FLAG_SINGLE_USE;
+    double partial[EB2_P_LEN];
+    g_data_flags = 0;
+    int rc = ksg_rows_once(dev, in, n, k, 0, n, partial, nullptr, nullptr, nullptr, general_only);
+    if (rc == EB2_ERR_RETRY_GENERAL) rc = ksg_rows_once(dev, in, n, k, 0, n, partial, nullptr, nullptr, nullptr, true);
+    status[t] = rc ? (rc | (g_data_flags << 8)) : 0;
+    values[t] = std::numeric_limits<double>::quiet_NaN();
+    if (!rc) eb2_ksg_mi_finish(partial, n, k, values + t);
+  };
+  if (!plan_ok || k + 1 > 8 || n < k2_min_rows() || getenv("EB2_NO_K2") || npairs == 0) {
+    for (int64_t t = 0; t < npairs; ++t) one_by_one(t, false);
+    return EB2_OK;
+  }
+  std::vector<Res> res(static_cast<size_t>(npairs));
+  const int rc = guarded(dev, [&](Ctx& c) {
+    Scratch s(c);
+    CU(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    record_event(s, c.ev[0]);
+    const int k1t = (k + 1 <= 4) ? 4 : 8;
+    ensure_psi_tab(s);
+    // 1. prepared variables (the reference's _rescale_data, ennemi/_driver.py:871-902) and their sample sorts
+    double* vals = s.dev<double>(static_cast<size_t>(nvar) * n);
+    int* colflags = s.dev<int>(nvar);
+    CU(cudaMemsetAsync(colflags, 0, sizeof(int) * nvar, st));
+    const size_t cbytes = k2::col_bytes(n);
+    char* cscratch = s.dev<char>(cbytes * nvar);
+    k2::Col* hcols = s.host<k2::Col>(nvar);
+    {
+      std::lock_guard<std::mutex> cache_guard(c.shared->mu);
+      auto& cache = c.shared->cache;
+      for (int v0 = 0; v0 < nvar; v0 += kMaxDimAny) {
+        const int m = std::min(kMaxDimAny, nvar - v0);
+        PrepArgs pa;
+        pa.d = m; pa.n = n; pa.raw = nullptr; pa.flags = nullptr;
+        for (int t = 0; t < m; ++t) {
+          const eb2_col_t& col = cols[v0 + t];
+          auto it = cache.find(col.key);
+          if (it == cache.end()) throw CudaFail{cudaErrorInvalidValue, "column key not in the device cache", __LINE__};
+          const int64_t last = col.off + (n - 1) * col.stride;
+          if (col.off < 0 || last < 0 || col.off >= it->second.second || last >= it->second.second)
+            throw CudaFail{cudaErrorInvalidValue, "column slice outside the cached column", __LINE__};
+          PrepCol& pc = pa.col[t];
+          pc.src = it->second.first; pc.off = col.off; pc.stride = col.stride; pc.mean = col.mean; pc.std = col.std;
+          pc.noise = nullptr; pc.noff = col.noff; pc.nstride = col.nstride; pc.dstats = nullptr;
+          if (col.nkey != 0) {
+            auto nt = cache.find(col.nkey);
+            if (nt == cache.end()) throw CudaFail{cudaErrorInvalidValue, "noise key not in the device cache", __LINE__};
+            const int64_t nlast = col.noff + (n - 1) * col.nstride;
+            if (col.noff < 0 || nlast < 0 || nlast >= nt->second.second)
+              throw CudaFail{cudaErrorInvalidValue, "noise slice outside the cached vector", __LINE__};
+            pc.noise = nt->second.first;
+          }
+          pc.flag = colflags + v0 + t;
+          pc.dst = vals + static_cast<int64_t>(v0 + t) * n;
+          hcols[v0 + t] = k2::carve_col(cscratch + cbytes * (v0 + t), n, pc.dst);
+          hcols[v0 + t].flag = pc.flag;
+        }
+        prep_kernel<<<cdiv(static_cast<int64_t>(m) * n, 256), 256, 0, st>>>(pa);
+        s.launches++;
+      }
+    }
+    k2::Col* dcols = s.dev<k2::Col>(nvar);
+    CU(cudaMemcpyAsync(dcols, hcols, sizeof(k2::Col) * nvar, cudaMemcpyHostToDevice, st));
+    CU(k2::colsort(dcols, nvar, plan, st, &s.launches));
+    record_event(s, c.ev[1]);
+    // 2. the pairs, in batches sized to a workspace budget
+    const size_t pbytes = k2::prob_bytes(plan, k1t);
+    size_t budget = size_t(3) << 30;
+    if (const char* e = getenv("EB2_PAIR_BATCH_MB")) budget = size_t(atoll(e)) << 20;     // tuning knob
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(npairs, static_cast<int64_t>(budget / pbytes)));
+    char* pscratch = s.dev<char>(pbytes * batch);
+    double* outs = s.dev<double>(static_cast<size_t>(npairs) * 8);
+    CU(cudaMemsetAsync(outs, 0, sizeof(double) * 8 * npairs, st));
+    k2::Prob* dprobs = s.dev<k2::Prob>(batch);
+    const k2::Shard whole{0, n, n};
+    for (int64_t p0 = 0; p0 < npairs; p0 += batch) {
+      const int m = static_cast<int>(std::min<int64_t>(batch, npairs - p0));
+      k2::Prob* hp = s.host<k2::Prob>(m);
+      for (int t = 0; t < m; ++t) {
+        hp[t] = k2::carve_prob(pscratch + pbytes * t, plan, k1t, pairs[2 * (p0 + t)], pairs[2 * (p0 + t) + 1]);
+        hp[t].out = outs + 8 * (p0 + t);
+      }
+      CU(cudaMemcpyAsync(dprobs, hp, sizeof(k2::Prob) * m, cudaMemcpyHostToDevice, st));
+      CU(k2::layout(dcols, dprobs, m, plan, st, &s.launches));
+      CU(k2::knn(dcols, dprobs, m, plan, k, whole, c.sm_count, st, &s.launches));
+      CU(k2::count_psi(dcols, dprobs, m, plan, whole, c.psi_tab, kPsiTab, st, &s.launches));
+      CU(k2::finalize(dcols, dprobs, m, plan, st, &s.launches));
+    }
+    record_event(s, c.ev[2]);
+    record_event(s, c.ev[3]);
+    record_event(s, c.ev[4]);
+    static_assert(sizeof(Res) <= 8 * sizeof(double), "result block");
+    std::vector<double> hout(static_cast<size_t>(npairs) * 8);
+    CU(cudaMemcpyAsync(hout.data(), outs, sizeof(double) * 8 * npairs, cudaMemcpyDeviceToHost, st));
+    record_event(s, c.ev[5]);
+    CU(cudaStreamSynchronize(st));
+    read_phase_times(c);
+    c.last_launches = s.launches;
+    for (int64_t t = 0; t < npairs; ++t) std::memcpy(&res[t], hout.data() + 8 * t, sizeof(Res));
+    return EB2_OK;
+  });
+  if (rc) return rc;
+  for (int64_t t = 0; t < npairs; ++t) {
+    const Res& h = res[t];
+    values[t] = std::numeric_limits<double>::quiet_NaN();
+    if (h.nonfinite & k2::kFlagOverflow) {
+      one_by_one(t, true);                 // heavily tied data: the general path takes this pair
+    } else if (h.nonfinite) {
+      status[t] = EB2_ERR_NONFINITE | ((h.nonfinite & 0xff) << 8);
+    } else {
+      status[t] = 0;
+      double partial[EB2_P_LEN] = {0};
+      partial[EB2_P_SUM] = h.v[0]; partial[EB2_P_ZERO_A] = h.v[1]; partial[EB2_P_ZERO_B] = h.v[2]; partial[EB2_P_ZERO_C] = h.v[3];
+      eb2_ksg_mi_finish(partial, n, k, values + t);
+    }
+  }
+  return EB2_OK;
 }
 
 // ---- a2: Frenzel-Pompe ----------------------------------------------------------------------------

@@ -187,6 +187,13 @@ EB2_API int eb2_last_data_flags(void);
 EB2_API int eb2_mi_cols_batch(int dev, const eb2_col_t* cols, int64_t ntasks, int c, int64_t n, int k, uint32_t flags,
                               double* values, int* status);
 
+/* a7 for pairwise_mi (the task list of ennemi/_driver.py:703-707 in ONE call): npairs bivariate estimates over a set
+ * of nvar prepared variables; pair t is (x = cols[pairs[2t]], y = cols[pairs[2t+1]]).  Every variable is rescaled and
+ * sorted once, the pairs run through the estimator in batches (one launch per stage for a whole batch).  values[t] /
+ * status[t] as in eb2_mi_cols_batch. */
+EB2_API int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pairs, int64_t npairs, int64_t n, int k,
+                             uint32_t flags, double* values, int* status);
+
 /* roofline denominator: FP64 (DADD) instructions per second this device retires, in 10^12/s,
  * measured with a register-resident kernel (best of 5).  The all-pairs kernels are bound by it. */
 EB2_API int eb2_measure_fp64_peak(int dev, double* tera_instr_per_s);

@@ -41,7 +41,7 @@ class OracleBackend:
 
     PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
                "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch", "cache_stats",
-               "cache_put_block", "cache_stats_many")
+               "cache_put_block", "cache_stats_many", "ksg_mi_pairs")
 
     def __init__(self, backend="scipy"):
         import oracle
@@ -138,6 +138,9 @@ class OracleBackend:
             except _native.NonFiniteInput as e:
                 status[t] = _native.ERR_NONFINITE | ((1 if e.nan else 2) << 8)
         return values, status
+
+    def ksg_mi_pairs(self, cols, pairs, n, k, dev=0, flags=0):
+        return self.mi_cols_batch([[cols[i], cols[j]] for i, j in np.asarray(pairs).reshape(-1, 2)], n, k, dev, flags)
 
     def cmi_cols(self, descs, n, k, dev=0, flags=0):
         rows = self._gather(descs, n, dev, flags)
