@@ -22,7 +22,7 @@ FLAG_SINGLE_USE = 8
 FLAG_DEVICE_STATS = 16
 
 ERR_CUDA, ERR_ARG, ERR_NONFINITE, ERR_UNSUPPORTED, ERR_CONSTANT = 1, 2, 3, 4, 5
-P_LEN = 8
+P_LEN = 16
 P_SUM, P_ZERO_A, P_ZERO_B, P_ZERO_C, P_ROWS, P_PAIRS = 0, 1, 2, 3, 4, 5
 
 # every symbol include/ennemi_b200.h declares (tests check the library exports all of them)
@@ -35,7 +35,7 @@ EXPORTS = (
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
-    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs",
+    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs", "eb2_last_pipeline",
 )
 
 _lib = None
@@ -315,6 +315,11 @@ def last_timing(dev: int = 0) -> dict:
         _raise(rc)
     return {"total_ms": ms[0], "knn_ms": ms[1], "count_ms": ms[2], "psi_ms": ms[3], "layout_ms": ms[4],
             "launches": launches.value}
+
+
+def last_pipeline(dev: int = 0) -> int:
+    """1 if the last KSG call on ``dev`` ran on the bivariate pipeline, 0 if the general path took it."""
+    return int(load().eb2_last_pipeline(dev))
 
 
 def measure_fp64_peak(dev: int = 0) -> float:

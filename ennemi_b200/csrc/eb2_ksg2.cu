@@ -1,14 +1,13 @@
-// ennemi_b200 — kernels of the bivariate KSG pipeline (sm_100a).  See eb2_ksg2.h for the data layout.
+// ennemi_b200 — kernels of the bivariate KSG pipeline (sm_100a): sort-free adaptive grid.  Data layout: eb2_ksg2.h.
 //
 // What each stage replaces in the reference (ennemi/_entropy_estimators.py):
-//   colsort + layout   the three cKDTree builds (:100-102)
+//   colgrid + layout   the three cKDTree builds (:100-102)
 //   knn                grid.query(xy, k=[k+1], p=inf)                         (:108)
 //   count_psi          x_grid / y_grid.query_ball_point(.., eps - 1e-12, p=inf, return_length=True) and the
 //                      digamma terms of the mean                              (:109-110, :113, :327-350)
 // Bit-exactness rules are those of eb2_kernels.cuh: one rounded fp64 subtraction per coordinate, exact
-// comparisons, conservative (widened) brackets decided by the exact per-candidate test.
-#include <cub/block/block_merge_sort.cuh>
-
+// comparisons; cell ranges are conservative (thresholds widened by 2^-50 relative) and every value in a boundary
+// cell is decided by the exact predicate.
 #include <algorithm>
 #include <cstdlib>
 
@@ -21,461 +20,619 @@ namespace k2 {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSortThreads = 512;
-constexpr int kSplitThreads = 1024;
-constexpr int kSplitItems = 8;                 // kSplitThreads * kSplitItems = 8,192 samples at most
-constexpr int kCountRows = 2048;               // rows per CTA of the bucket count / scatter kernels
-constexpr int kPiece = 128;                    // slots of a chunk window staged per warp at a time
-constexpr int kSeed = 4;                       // slots on either side of a query's own slot that seed its list
-constexpr int kWarps = 8;                      // warps per CTA of the search kernels
+constexpr int kSplitThreads = 512;
+constexpr int kSplitItems = 8;                 // kSplitThreads * kSplitItems = 4,096 samples at most
+constexpr int kHistRows = 2048;                // rows per CTA of the bucket histogram / scatter kernels
+constexpr int kThreadsB = 256;                 // threads per CTA everywhere else
 constexpr double kSlack = 8.881784197001252e-16;   // 2^-50
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 __device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-  return v;
-}
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
-  return v;
+// floor((v - lo) * sc) clamped to [0, ncell - 1]: monotone non-decreasing in v (rounded subtraction, multiplication
+// by a non-negative scale, truncation and clamping all are).  The one function cells are built AND queried with.
+__device__ __forceinline__ int lin_cell(double v, double lo, double sc, int ncell) {
+  const double t = (v - lo) * sc;
+  if (!(t > 0.0)) return 0;                    // (also 0 * inf = NaN when the map is degenerate: one cell)
+  if (t >= (double)ncell) return ncell - 1;
+  return (int)t;
 }
 
-// (value, row): a total order, so that every sort below has ONE possible result (deterministic layouts)
-struct KV {
-  double v;
-  int r;
-  int pad;
+// bucket of v: quantile stretch c = number of splitters below v, cut linearly into kSub parts
+struct BucketFn {
+  const double* split;
+  const double* clo;
+  const double* csc;
+  int Bc;
 };
-struct KVLess {
-  __device__ __forceinline__ bool operator()(const KV& a, const KV& b) const { return a.v < b.v || (a.v == b.v && a.r < b.r); }
-};
-struct DLess {
-  __device__ __forceinline__ bool operator()(double a, double b) const { return a < b; }
-};
-
-// bucket of v: number of splitters strictly below it
-__device__ __forceinline__ int bucket_of(const double* split, int nsplit, double v) {
-  int lo = 0, hi = nsplit;
+__device__ __forceinline__ int bucket_fn(const BucketFn& f, double v) {
+  int lo = 0, hi = f.Bc - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (split[mid] < v) lo = mid + 1; else hi = mid;
+    if (f.split[mid] < v) lo = mid + 1; else hi = mid;
   }
-  return lo;
+  return lo * kSub + lin_cell(v, f.clo[lo], f.csc[lo], kSub);
 }
 
-// sum of count[0 .. b) and of the same counts rounded up to 32, by the whole CTA (b <= kMaxBuckets)
-__device__ __forceinline__ void bucket_offsets(const int* count, int b, int* red /* 2 * 32 ints */, int& rank_off, int& slot_off) {
-  int a = 0, s = 0;
-  for (int i = threadIdx.x; i < b; i += blockDim.x) {
-    const int c = count[i];
-    a += c;
-    s += (c + 31) & ~31;
+// in-place exclusive prefix sum of a[0 .. m) in shared memory, m <= 16 * blockDim.x, by the whole CTA;
+// returns the total.  red: 32 ints of shared scratch.
+__device__ __forceinline__ int block_excl_scan(int* a, int m, int* red) {
+  const int per = (m + blockDim.x - 1) / blockDim.x;
+  const int lo = min(m, (int)threadIdx.x * per), hi = min(m, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
   }
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 31) red[w] = inc;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int i = 0; i < nw; ++i) {
+    if (i < w) base += red[i];
+    total += red[i];
+  }
+  int run = base + inc - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+// block-wide minimum and maximum of finite doubles (every thread gets both); red: 64 doubles of shared scratch
+__device__ __forceinline__ void block_minmax(double& mn, double& mx, double* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(kFull, a, o);
-    s += __shfl_xor_sync(kFull, s, o);
+    mn = fmin(mn, __shfl_xor_sync(kFull, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
-  if (l == 0) { red[w] = a; red[32 + w] = s; }
+  if ((threadIdx.x & 31) == 0) { red[w] = mn; red[32 + w] = mx; }
   __syncthreads();
-  a = 0; s = 0;
-  for (int i = 0; i < nw; ++i) { a += red[i]; s += red[32 + i]; }
-  rank_off = a;
-  slot_off = s;
+  mn = red[0]; mx = red[32];
+  for (int i = 1; i < nw; ++i) { mn = fmin(mn, red[i]); mx = fmax(mx, red[32 + i]); }
+  __syncthreads();
 }
 
-// ---- colsort 1: splitters from a sorted regular sample ---------------------------------------------------------
-__global__ void __launch_bounds__(kSplitThreads) split_kernel(const Col* cols, long long n, int B, int over) {
-  using Sort = cub::BlockMergeSort<double, kSplitThreads, kSplitItems>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(smem_raw);
+// ---- colgrid 1: the bucket function from a sorted regular sample ------------------------------------------------
+// The S <= 4,096 sample values are ranked by counting, spread over the GPU: a CTA owns 32 samples (one per lane), its
+// eight warps each compare them with an eighth of all samples (every lane reads the same shared-memory word: a
+// broadcast), and the sample is written to its rank.  Ties are broken by sample index, so the ranks are a permutation.
+constexpr int kRankThreads = 256;
+__global__ void __launch_bounds__(kRankThreads) sample_gather_kernel(const Col* cols, long long n, int S) {
+  const Col c = cols[blockIdx.y];
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= S) return;
+  // sample g sits in the middle of the g-th of S equal stretches of the column
+  double v = c.vals[(long long)(((2 * (long long)g + 1) * n) / (2 * (long long)S))];
+  if (!(fabs(v) < d_inf())) v = d_inf();        // non-finite input: reported by the histogram kernel
+  c.sraw[g] = v;
+}
+
+__global__ void __launch_bounds__(kRankThreads) sample_rank_kernel(const Col* cols, int S) {
+  __shared__ double sk[kSplitThreads * kSplitItems];
+  __shared__ int part[kRankThreads / 32][32];
+  const Col c = cols[blockIdx.y];
+  for (int g = threadIdx.x; g < S; g += blockDim.x) sk[g] = c.sraw[g];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + lane;
+  const double v = g < S ? sk[g] : d_inf();
+  const int per = (S + 7) / 8;
+  const int j0 = warp * per, j1 = min(S, j0 + per);
+  int cnt = 0;
+  for (int j = j0; j < j1; ++j) {
+    const double u = sk[j];
+    cnt += (int)(u < v || (u == v && j < g));
+  }
+  part[warp][lane] = cnt;
+  __syncthreads();
+  if (warp == 0 && g < S) {
+    int r = 0;
+#pragma unroll
+    for (int w = 0; w < kRankThreads / 32; ++w) r += part[w][lane];
+    c.ssort[r] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kSplitThreads) split_tables_kernel(const Col* cols, int Bc, int over, int NB) {
   const Col c = cols[blockIdx.x];
-  const int S = B * over;
-  double key[kSplitItems];
-#pragma unroll
-  for (int i = 0; i < kSplitItems; ++i) {
-    const int g = threadIdx.x * kSplitItems + i;
-    // sample g sits in the middle of the g-th of S equal stretches of the column
-    key[i] = g < S ? c.vals[(long long)(((2 * (long long)g + 1) * n) / (2 * (long long)S))] : d_inf();
-    if (key[i] != key[i]) key[i] = d_inf();      // NaN input: reported by the count kernel, must not upset the sort
+  const int S = Bc * over;
+  const double* sk = c.ssort;
+  for (int q = threadIdx.x; q < Bc; q += blockDim.x) {
+    const double lo = q == 0 ? sk[0] : sk[q * over - 1];
+    const double hi = q == Bc - 1 ? sk[S - 1] : sk[(q + 1) * over - 1];
+    c.clo[q] = lo;
+    c.csc[q] = (hi > lo && hi - lo < d_inf()) ? (double)kSub / (hi - lo) : 0.0;
+    if (q < Bc - 1) c.split[q] = hi;
   }
-  if (B > 1) {
-    Sort(tmp).Sort(key, DLess(), S, d_inf());
-#pragma unroll
-    for (int i = 0; i < kSplitItems; ++i) {
-      const int g = threadIdx.x * kSplitItems + i;
-      if (g < S && (g + 1) % over == 0) {
-        const int j = (g + 1) / over - 1;
-        if (j < B - 1) c.split[j] = key[i];
-      }
-    }
-  }
-  for (int b = threadIdx.x; b < kMaxBuckets; b += blockDim.x) { c.count[b] = 0; c.fill[b] = 0; }
+  for (int b = threadIdx.x; b <= NB; b += blockDim.x) { c.count[b] = 0; c.fill[b] = 0; }
 }
 
-// ---- colsort 2: bucket of every row, rows per bucket -------------------------------------------------------------
-__global__ void __launch_bounds__(256) bucket_count_kernel(const Col* cols, long long n, int B) {
-  __shared__ double s_split[kMaxBuckets];
+// ---- colgrid 2: bucket of every row, rows per bucket ---------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsB) bucket_hist_kernel(const Col* cols, long long n, int Bc, int NB) {
+  __shared__ double s_split[kMaxCoarse], s_clo[kMaxCoarse], s_csc[kMaxCoarse];
   __shared__ int s_hist[kMaxBuckets];
   const Col c = cols[blockIdx.y];
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    s_split[b] = b < B - 1 ? c.split[b] : d_inf();
-    s_hist[b] = 0;
+  for (int q = threadIdx.x; q < Bc; q += blockDim.x) {
+    s_split[q] = q < Bc - 1 ? c.split[q] : d_inf();
+    s_clo[q] = c.clo[q];
+    s_csc[q] = c.csc[q];
   }
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) s_hist[b] = 0;
   __syncthreads();
-  const long long r0 = (long long)blockIdx.x * kCountRows;
+  const BucketFn fn{s_split, s_clo, s_csc, Bc};
+  const long long r0 = (long long)blockIdx.x * kHistRows;
   bool bad = false;
-#pragma unroll
-  for (int i = 0; i < kCountRows / 256; ++i) {
-    const long long r = r0 + i * 256 + threadIdx.x;
+#pragma unroll 4
+  for (int i = 0; i < kHistRows / kThreadsB; ++i) {
+    const long long r = r0 + i * kThreadsB + threadIdx.x;
     if (r < n) {
       const double v = c.vals[r];
       if (!(fabs(v) < d_inf())) bad = true;
-      const int b = bucket_of(s_split, B - 1, v);
-      c.bid[r] = (unsigned short)b;
+      const int b = bucket_fn(fn, v);
+      c.bkt[r] = (unsigned short)b;
       atomicAdd(&s_hist[b], 1);
     }
   }
   if (bad) atomicOr(c.flag, kFlagNonFinite);
   __syncthreads();
-  for (int b = threadIdx.x; b < B; b += blockDim.x)
+  for (int b = threadIdx.x; b < NB; b += blockDim.x)
     if (s_hist[b]) atomicAdd(&c.count[b], s_hist[b]);
 }
 
-// ---- colsort 3: scatter (value, row) into the buckets --------------------------------------------------------------
-__global__ void __launch_bounds__(256) bucket_scatter_kernel(const Col* cols, long long n, int B) {
-  __shared__ int s_off[kMaxBuckets];
-  __shared__ int s_warp[8];
+// ---- colgrid 3: rows and values grouped by bucket ------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsB) bucket_scatter_kernel(const Col* cols, long long n, int NB) {
+  __shared__ int s_boff[kMaxBuckets];
+  __shared__ int s_hist[kMaxBuckets];
+  __shared__ int s_base[kMaxBuckets];
+  __shared__ int red[32];
   const Col c = cols[blockIdx.y];
-  // exclusive scan of the bucket counts: 4 consecutive buckets per thread
-  {
-    int v[4], sum = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = threadIdx.x * 4 + i;
-      v[i] = b < B ? c.count[b] : 0;
-      sum += v[i];
-    }
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFull, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
-    }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < (threadIdx.x >> 5); ++w) base += s_warp[w];
-    int run = base + inc - sum;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = threadIdx.x * 4 + i;
-      if (b < kMaxBuckets) s_off[b] = run;
-      run += v[i];
-    }
-    __syncthreads();
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) { s_boff[b] = c.count[b]; s_hist[b] = 0; }
+  __syncthreads();
+  block_excl_scan(s_boff, NB, red);
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) c.boff[b] = s_boff[b];
+    if (threadIdx.x == 0) c.boff[NB] = (int)n;
   }
-  const long long r0 = (long long)blockIdx.x * kCountRows;
-#pragma unroll
-  for (int i = 0; i < kCountRows / 256; ++i) {
-    const long long r = r0 + i * 256 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * kHistRows;
+  for (int i = 0; i < kHistRows / kThreadsB; ++i) {
+    const long long r = r0 + i * kThreadsB + threadIdx.x;
+    if (r < n) atomicAdd(&s_hist[c.bkt[r]], 1);
+  }
+  __syncthreads();
+  // one reservation per (CTA, bucket); the order of the rows inside a bucket is irrelevant downstream
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) {
+    const int h = s_hist[b];
+    if (h) s_base[b] = s_boff[b] + atomicAdd(&c.fill[b], h);
+    s_hist[b] = 0;
+  }
+  __syncthreads();
+  for (int i = 0; i < kHistRows / kThreadsB; ++i) {
+    const long long r = r0 + i * kThreadsB + threadIdx.x;
     if (r < n) {
-      const int b = c.bid[r];
-      const int pos = s_off[b] + atomicAdd(&c.fill[b], 1);
-      c.st_val[pos] = c.vals[r];
-      c.st_row[pos] = (int)r;
+      const int b = c.bkt[r];
+      const int pos = s_base[b] + atomicAdd(&s_hist[b], 1);
+      c.srow[pos] = (int)r;
+      c.sval[pos] = c.vals[r];
     }
   }
 }
 
-// one bucket of (value, row) pairs, sorted by the CTA in shared memory
-template <int IPT, typename ValueT>
-struct BucketSort {
-  using Sort = cub::BlockMergeSort<KV, kSortThreads, IPT, ValueT>;
-};
-
-// ---- colsort 4: sort every bucket; per-bucket tables ---------------------------------------------------------------
-template <int IPT>
-__device__ __forceinline__ void sort_bucket_store(const Col& c, int off, int len, unsigned char* smem_raw) {
-  using Sort = cub::BlockMergeSort<KV, kSortThreads, IPT>;
-  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(smem_raw);
-  KV key[IPT];
-  const KV oob{d_inf(), 0x7fffffff, 0};
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int g = threadIdx.x * IPT + i;
-    key[i] = oob;
-    if (g < len) { key[i].v = c.st_val[off + g]; key[i].r = c.st_row[off + g]; }
-  }
-  Sort(tmp).Sort(key, KVLess(), len, oob);
-#pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int g = threadIdx.x * IPT + i;
-    if (g < len) { c.sorted[off + g] = key[i].v; c.perm[off + g] = key[i].r; }
-  }
-}
-
-__global__ void __launch_bounds__(kSortThreads) bucket_sort_kernel(const Col* cols, int B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int red[64];
+// ---- colgrid 4: the values of every bucket grouped into fine cells (about one per cell) ----------------------------
+// The cell map of bucket b is linear over the stretch the bucket function assigns to it (split[b-1], split[b]] (the
+// outermost sample values at the two ends; values beyond them clamp into the end cells).  vlo / vhi are bounds of the
+// bucket's values for the search kernels: values of bucket b lie in (vlo, vhi].
+static_assert(kSub == 1, "fine_cells_kernel takes the bucket bounds from the quantile stretches");
+__global__ void __launch_bounds__(kThreadsB) fine_cells_kernel(const Col* cols, long long n, int NB) {
+  __shared__ int s_hist[kMaxCells];
+  __shared__ int red[32];
   const Col c = cols[blockIdx.y];
   const int b = blockIdx.x;
-  const int len = c.count[b];
-  int off, soff;
-  bucket_offsets(c.count, b, red, off, soff);
-  if (threadIdx.x == 0) {
-    c.boff[b] = off;
-    c.soff[b] = soff;
-    if (b == B - 1) { c.boff[B] = off + len; c.soff[B] = soff + ((len + 31) & ~31); }
-    if (len > kBucketCap) atomicOr(c.flag, kFlagOverflow);
+  const int len = c.count[b], off = c.boff[b];
+  if (b == NB - 1 && threadIdx.x == 0) { c.fstart[n] = (int)n; c.fstart[n + 1] = (int)n; }
+  if (len > kBucketCap) {
+    if (threadIdx.x == 0) atomicOr(c.flag, kFlagOverflow);
+    return;
   }
-  if (len > kBucketCap || (*c.flag & (kFlagNonFinite | kFlagNaN))) return;
-  if (len > kSortThreads * 4) sort_bucket_store<8>(c, off, len, smem_raw);
-  else if (len > 0) sort_bucket_store<4>(c, off, len, smem_raw);
+  if (*c.flag & (kFlagNonFinite | kFlagNaN)) return;
+  const double lo = c.clo[b];
+  const int G = min(max(len, 1), kMaxCells);
+  const double sc = c.csc[b] * (double)G;                   // csc = 1 / width of the stretch (0: degenerate)
+  if (threadIdx.x == 0) {
+    c.vlo[b] = b == 0 ? -d_inf() : lo;
+    c.vhi[b] = b == NB - 1 ? d_inf() : c.split[b];
+    c.fsc[b] = sc;
+    c.ncell[b] = len ? G : 0;
+    c.fg[b] = FineGrid{lo, sc, off, len ? G : 0};
+  }
+  if (len == 0) return;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) s_hist[g] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // value range of the bucket; an empty bucket takes its upper splitter so that lo / hi stay non-decreasing
-    double lo, hi;
-    if (len > 0) { lo = c.sorted[off]; hi = c.sorted[off + len - 1]; }
-    else { lo = hi = (b < B - 1) ? c.split[b] : (B > 1 ? c.split[B - 2] : 0.0); }
-    c.lo[b] = lo;
-    c.hi[b] = hi;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) atomicAdd(&s_hist[lin_cell(c.sval[off + i], lo, sc, G)], 1);
+  __syncthreads();
+  block_excl_scan(s_hist, G, red);
+  for (int g = threadIdx.x; g < len; g += blockDim.x) c.fstart[off + g] = g < G ? off + s_hist[g] : off + len;
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const double v = c.sval[off + i];
+    const int pos = atomicAdd(&s_hist[lin_cell(v, lo, sc, G)], 1);
+    c.fval[off + pos] = v;
   }
 }
 
-// ---- layout: the rows of every x-bucket in ascending y -------------------------------------------------------------
-template <int IPT>
-__device__ __forceinline__ void layout_bucket(const Col& cx, const Col& cy, const Prob& pr, int off, int soff, int len,
-                                              unsigned char* smem_raw) {
-  using Sort = cub::BlockMergeSort<KV, kSortThreads, IPT, double>;
-  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(smem_raw);
-  KV key[IPT];
-  double xval[IPT];
-  const KV oob{d_inf(), 0x7fffffff, 0};
+// ---- layout: the rows of every x-bucket grouped into cells of the bucket's own y range (about one per cell) ---------
+constexpr int kLayoutThreads = 512;
+constexpr int kLayoutItems = 8;       // rows per thread kept in registers: buckets of up to 4,096 rows gather y once
+
+__global__ void __launch_bounds__(kLayoutThreads, 2) layout_kernel(const Col* cols, const Prob* probs, long long n, int NB) {
+  __shared__ int s_hist[kMaxCells];
+  __shared__ double redd[64];
+  __shared__ int red[32];
+  const Prob pr = probs[blockIdx.y];
+  const Col cx = cols[pr.cx], cy = cols[pr.cy];
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) {
+    *pr.left_count = 0u;
+    pr.acc[0] = 0ull; pr.acc[1] = 0ull; pr.acc[2] = 0ull; pr.acc[3] = 0ull;
+  }
+  if ((*cx.flag | *cy.flag) != 0) return;
+  const int len = cx.count[b], off = cx.boff[b];
+  if (b == NB - 1 && threadIdx.x == 0) { pr.cstart[n] = (int)n; pr.cstart[n + 1] = (int)n; }
+  if (len == 0) {
+    if (threadIdx.x == 0) { pr.bymin[b] = 0.0; pr.bysc[b] = 0.0; }
+    return;
+  }
+  const bool fast = len <= kLayoutItems * kLayoutThreads;
+  double yv[kLayoutItems];
+  int rv[kLayoutItems], cv[kLayoutItems];
+  double mn = d_inf(), mx = -d_inf();
+  if (fast) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int g = threadIdx.x * IPT + i;
-    key[i] = oob;
-    xval[i] = d_nan();
-    if (g < len) {
-      const int r = cx.perm[off + g];
-      key[i].v = cy.vals[r];
-      key[i].r = r;
-      xval[i] = cx.sorted[off + g];
+    for (int u = 0; u < kLayoutItems; ++u) {
+      const int i = threadIdx.x + u * kLayoutThreads;
+      rv[u] = i < len ? cx.srow[off + i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kLayoutItems; ++u) {
+      const int i = threadIdx.x + u * kLayoutThreads;
+      yv[u] = cy.vals[rv[u]];
+      if (i < len) { mn = fmin(mn, yv[u]); mx = fmax(mx, yv[u]); }
+    }
+  } else {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const double y = cy.vals[cx.srow[off + i]];
+      mn = fmin(mn, y);
+      mx = fmax(mx, y);
     }
   }
-  Sort(tmp).Sort(key, xval, KVLess(), len, oob);
-  const int padded = (len + 31) & ~31;
+  block_minmax(mn, mx, redd);
+  const int F = min(len, kMaxCells);
+  const double sc = (mx > mn && mx - mn < d_inf()) ? (double)F / (mx - mn) : 0.0;
+  if (threadIdx.x == 0) { pr.bymin[b] = mn; pr.bysc[b] = sc; }
+  for (int f = threadIdx.x; f < F; f += blockDim.x) s_hist[f] = 0;
+  __syncthreads();
+  if (fast) {
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const int g = threadIdx.x * IPT + i;
-    if (g < len) {
-      pr.px[soff + g] = xval[i];
-      pr.py[soff + g] = key[i].v;
-      pr.slot_row[soff + g] = key[i].r;
-    } else if (g < padded) {
-      pr.px[soff + g] = d_nan();
-      pr.py[soff + g] = d_nan();
-      pr.slot_row[soff + g] = -1;
+    for (int u = 0; u < kLayoutItems; ++u) {
+      const int i = threadIdx.x + u * kLayoutThreads;
+      cv[u] = lin_cell(yv[u], mn, sc, F);
+      if (i < len) atomicAdd(&s_hist[cv[u]], 1);
+    }
+  } else {
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+      atomicAdd(&s_hist[lin_cell(cy.vals[cx.srow[off + i]], mn, sc, F)], 1);
+  }
+  __syncthreads();
+  block_excl_scan(s_hist, F, red);
+  for (int f = threadIdx.x; f < len; f += blockDim.x) pr.cstart[off + f] = f < F ? off + s_hist[f] : off + len;
+  __syncthreads();
+  if (fast) {
+#pragma unroll
+    for (int u = 0; u < kLayoutItems; ++u) {
+      const int i = threadIdx.x + u * kLayoutThreads;
+      if (i < len) {
+        const int pos = off + atomicAdd(&s_hist[cv[u]], 1);
+        pr.px[pos] = cx.sval[off + i];
+        pr.py[pos] = yv[u];
+        pr.prow[pos] = rv[u];
+        pr.pbkt[pos] = (unsigned short)b;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const int r = cx.srow[off + i];
+      const double y = cy.vals[r];
+      const int pos = off + atomicAdd(&s_hist[lin_cell(y, mn, sc, F)], 1);
+      pr.px[pos] = cx.sval[off + i];
+      pr.py[pos] = y;
+      pr.prow[pos] = r;
+      pr.pbkt[pos] = (unsigned short)b;
     }
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads) layout_kernel(const Col* cols, const Prob* probs, int B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// ---- knn ---------------------------------------------------------------------------------------------------------------
+constexpr int kHitCap = 8;            // slots a thread notes down before it folds them into its list
+
+// Slots [a, e) against one query.  The scan itself is branch-free per group of four (the eight loads of a group are
+// independent and in flight together): slots that pass the exact test against the threshold of the moment are only
+// NOTED (their index, in a per-thread strip of shared memory); the noted slots are folded into the sorted list when the
+// strip fills up and at the end, re-tested against the threshold as it stands then.  A warp's lanes hit at different
+// slots: noting keeps them in step where inserting on the spot would serialise them.
+template <int K1T, bool GATED>
+__device__ __forceinline__ void scan_slots(const double* __restrict__ px, const double* __restrict__ py, int a, int e,
+                                           double qx, double qy, double (&best)[K1T], double& thr, unsigned long long& np,
+                                           double gate, int* hit) {
+  if (e > a) np += (unsigned long long)(e - a);
+  constexpr int G = 4;
+  int cnt = 0;
+  auto fold = [&]() {
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+      const int t = hit[i * kThreadsB];
+      const double xv = px[t], yv = py[t];
+      if (fabs(qx - xv) < thr && fabs(qy - yv) < thr) {
+        topk_insert<K1T>(best, fmax(fabs(qx - xv), fabs(qy - yv)));
+        thr = GATED ? fmin(best[K1T - 1], gate) : best[K1T - 1];
+      }
+    }
+    cnt = 0;
+  };
+#pragma unroll 1
+  for (int s = a; s < e; s += G) {
+    double xv[G], yv[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int t = min(s + u, e - 1);             // the last group repeats its final slot; repeats are masked below
+      xv[u] = px[t];
+      yv[u] = py[t];
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const bool pass = s + u < e && fabs(qx - xv[u]) < thr && fabs(qy - yv[u]) < thr;
+      if (pass) hit[cnt * kThreadsB] = s + u;
+      cnt += (int)pass;
+    }
+    if (cnt > kHitCap - G) fold();
+  }
+  fold();
+}
+
+// every row of x-bucket [off, off + len) whose y can lie within thr of qy (the cells the widened window touches);
+// slots [skip_a, skip_e) have been examined already
+template <int K1T, bool GATED>
+__device__ __forceinline__ void visit_bucket(const Prob& pr, int off, int len, double ymin, double sc, double qx, double qy,
+                                             double (&best)[K1T], double& thr, unsigned long long& np, int skip_a, int skip_e,
+                                             double gate, int* hit) {
+  int a = off, e = off + len;
+  if (thr < d_inf()) {
+    const int F = min(len, kMaxCells);
+    const double lo_v = (qy - thr) - (fabs(qy) + thr) * kSlack;
+    const double hi_v = (qy + thr) + (fabs(qy) + thr) * kSlack;
+    const int f_lo = lin_cell(lo_v, ymin, sc, F), f_hi = lin_cell(hi_v, ymin, sc, F);
+    a = pr.cstart[off + f_lo];
+    if (f_hi + 1 < F) e = pr.cstart[off + f_hi + 1];
+  }
+  if (skip_a < skip_e) {
+    scan_slots<K1T, GATED>(pr.px, pr.py, a, min(e, skip_a), qx, qy, best, thr, np, gate, hit);
+    scan_slots<K1T, GATED>(pr.px, pr.py, max(a, skip_e), e, qx, qy, best, thr, np, gate, hit);
+  } else {
+    scan_slots<K1T, GATED>(pr.px, pr.py, a, e, qx, qy, best, thr, np, gate, hit);
+  }
+}
+
+// window of x-bucket [off, off + len) whose y can lie within thr of qy: the slots of the cells the widened window touches
+__device__ __forceinline__ void bucket_window(const Prob& pr, int off, int len, double ymin, double sc, double qy, double thr,
+                                              int& a, int& e) {
+  a = off;
+  e = off + len;
+  if (thr < d_inf()) {
+    const int F = min(len, kMaxCells);
+    const double lo_v = (qy - thr) - (fabs(qy) + thr) * kSlack;
+    const double hi_v = (qy + thr) + (fabs(qy) + thr) * kSlack;
+    const int f_lo = lin_cell(lo_v, ymin, sc, F), f_hi = lin_cell(hi_v, ymin, sc, F);
+    a = pr.cstart[off + f_lo];
+    if (f_hi + 1 < F) e = pr.cstart[off + f_hi + 1];
+  }
+}
+
+// Slots [a, e) against one query, in groups of four (eight independent loads in flight, one branch per group).  When a
+// slot of the group passes the exact test, the group's distances are inserted smallest first until the next one no longer
+// beats the k-th distance of the moment - almost always one insertion, so the lanes of a warp (which hit at different
+// slots) spend little time waiting for each other.
+// Slots [skip_a, skip_e) (the seeds) are jumped over.
+template <int K1T>
+__device__ __forceinline__ void scan_range(const double* __restrict__ px, const double* __restrict__ py, int a, int e,
+                                           double qx, double qy, double (&best)[K1T], double& thr, unsigned long long& np,
+                                           int skip_a = 0, int skip_e = 0) {
+  if (e > a) np += (unsigned long long)(e - a);
+  const double kInf = d_inf();
+  if (a >= skip_a && a < skip_e) a = skip_e;
+#pragma unroll 1
+  for (int s = a; s < e; s += 4) {
+    if (s >= skip_a && s < skip_e) s = skip_e;   // (the group that straddles the start of the seeds masks them below)
+    double dx[4], dy[4];
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = min(s + u, e - 1);           // the last group repeats its final slot; repeats are masked below
+      const bool seeded = t >= skip_a && t < skip_e;
+      dx[u] = seeded ? kInf : fabs(qx - px[t]);
+      dy[u] = fabs(qy - py[t]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) any = any || (s + u < e && dx[u] < thr && dy[u] < thr);
+    if (any) {
+      double d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = (s + u < e) ? fmax(dx[u], dy[u]) : kInf;
+#pragma unroll 1
+      for (int rep = 0; rep < 4; ++rep) {
+        double m = d[0];
+        int w = 0;
+#pragma unroll
+        for (int u = 1; u < 4; ++u) {
+          const bool lt = d[u] < m;
+          m = lt ? d[u] : m;
+          w = lt ? u : w;
+        }
+        if (!(m < thr)) break;                    // (max(dx, dy) < thr  <=>  both differences below thr: the exact test)
+        topk_insert<K1T>(best, m);
+        thr = best[K1T - 1];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = (u == w) ? kInf : d[u];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void cmp_swap(double& x, double& y) {
+  const bool sw = y < x;
+  const double lo = sw ? y : x, hi = sw ? x : y;
+  x = lo;
+  y = hi;
+}
+
+// One thread per query, every lane of a warp in the same step of the search at the same time:
+//   1. eight slots around the query's own (its neighbours in y inside the bucket, itself included at distance 0) are
+//      sorted by a fixed 19-comparator network: the list starts full, no branches
+//   2. the rest of the home bucket's window
+//   3. up to `near` non-empty buckets to the right, nearest first, while the gap in x is below the current k-th distance
+//      (rounded subtraction is monotone => exact), then the same to the left
+// Queries that need more buckets (sparse regions of y: their k-th distance spans many buckets of x) are handed to the
+// leftover kernel, which deals the buckets of ONE query to the lanes of a warp.
+template <int K1T>
+__global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const Prob* probs, long long n, int NB, int k, int near,
+                                                          unsigned left_cap, const Shard sh) {
   const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
-  const int b = blockIdx.x;
-  const int len = cx.count[b], off = cx.boff[b], soff = cx.soff[b];
-  if (b == 0 && threadIdx.x == 0) *pr.left_count = 0u;
-  if (len > kSortThreads * 4) layout_bucket<8>(cx, cy, pr, off, soff, len, smem_raw);
-  else if (len > 0) layout_bucket<4>(cx, cy, pr, off, soff, len, smem_raw);
-}
-
-// blocks [blo, bhi) of `nblocks` that belong to the shard: block b maps to row floor(b * n / nblocks)
-__device__ __forceinline__ void shard_blocks(const Shard& sh, int nblocks, int& blo, int& bhi) {
-  // smallest b with floor(b * n / nblocks) >= row  <=>  b >= ceil(row * nblocks / n)
-  blo = (int)((sh.row_lo * (long long)nblocks + sh.n - 1) / sh.n);
-  bhi = (int)((sh.row_hi * (long long)nblocks + sh.n - 1) / sh.n);
-  if (sh.row_hi >= sh.n) bhi = nblocks;
-  if (blo > nblocks) blo = nblocks;
-  if (bhi > nblocks) bhi = nblocks;
-}
-
-// Every lane that wants the chunk walks ITS OWN window of the chunk's ascending y (exact predicates on rounded
-// differences: monotone in the slot index); the warp-wide bracket of those windows is staged through shared memory in
-// pieces.  Slots within kSeed of own_rel were examined when the list was seeded and must not enter it twice.
-template <int K1T>
-__device__ __forceinline__ void scan_chunk(int len, const double* __restrict__ gx, const double* __restrict__ gy, bool want,
-                                           int own_rel, double qx, double qy, double (&best)[K1T], double& thr,
-                                           unsigned long long& np, double* sx, double* sy, int lane) {
-  if (len == 0) return;
+  const int lane = threadIdx.x & 31;
+  const long long s64 = (long long)blockIdx.x * kThreadsB + threadIdx.x;
+  const int slot = (int)min(s64, n - 1);
+  const int b = pr.pbkt[slot];
+  const int off = cx.boff[b];
+  const bool valid = s64 < n && off >= sh.row_lo && off < sh.row_hi;      // the shard owns whole buckets
   const double kInf = d_inf();
-  const double t = warp_max(want ? thr : 0.0);
-  int a = 0, b = len;
-  if (t < kInf) {
-    const double y0 = warp_min(want ? qy : kInf), y1 = warp_max(want ? qy : -kInf);
-    const double lo_v = (y0 - t) - (fabs(y0) + t) * kSlack;
-    const double hi_v = (y1 + t) + (fabs(y1) + t) * kSlack;
-    a = warp_first_true(0, len, [&](int s) { return !(gy[s] < lo_v); });
-    b = warp_first_true(a, len, [&](int s) { return gy[s] > hi_v; });
+  const double* __restrict__ px = pr.px;
+  const double* __restrict__ py = pr.py;
+  const double qx = px[slot], qy = py[slot];
+  const int len = cx.count[b];
+  unsigned long long np = 0;
+  // 1. seeds
+  const int sa = max(off, min(slot - 4, off + len - 8));
+  const int se = min(sa + 8, off + len);
+  double d[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int t = min(sa + u, se - 1);
+    const double v = fmax(fabs(qx - px[t]), fabs(qy - py[t]));
+    d[u] = (valid && sa + u < se) ? v : kInf;
   }
-  for (int p0 = a; p0 < b; p0 += kPiece) {
-    const int pl = min(kPiece, b - p0);
-    for (int u = lane; u < pl; u += 32) { sx[u] = gx[p0 + u]; sy[u] = gy[p0 + u]; }
-    __syncwarp();
-    if (want) {
-      int lo = 0, hi = pl;
-      const double t0 = thr;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((qy - sy[mid]) < t0) hi = mid; else lo = mid + 1;
+  cmp_swap(d[0], d[1]); cmp_swap(d[2], d[3]); cmp_swap(d[4], d[5]); cmp_swap(d[6], d[7]);
+  cmp_swap(d[0], d[2]); cmp_swap(d[1], d[3]); cmp_swap(d[4], d[6]); cmp_swap(d[5], d[7]);
+  cmp_swap(d[1], d[2]); cmp_swap(d[5], d[6]); cmp_swap(d[0], d[4]); cmp_swap(d[3], d[7]);
+  cmp_swap(d[1], d[5]); cmp_swap(d[2], d[6]);
+  cmp_swap(d[1], d[4]); cmp_swap(d[3], d[6]);
+  cmp_swap(d[2], d[4]); cmp_swap(d[3], d[5]);
+  cmp_swap(d[3], d[4]);
+  double best[K1T];
+#pragma unroll
+  for (int t = 0; t < K1T; ++t) best[t] = d[t];
+  double thr = best[K1T - 1];
+  if (valid) np += (unsigned long long)(se - sa);
+  // 2. the rest of the home bucket
+  {
+    int a = 0, e = 0;
+    if (valid) bucket_window(pr, off, len, pr.bymin[b], pr.bysc[b], qy, thr, a, e);
+    scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np, sa, se);
+  }
+  // 3. outwards
+  int rstart = NB, lend = 0;
+  {
+    bool more = valid;
+    int j = b + 1;
+    for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
+      int a = 0, e = 0;
+      if (more) {
+        int lj = 0;
+        while (j < NB && (lj = cx.count[j]) == 0) ++j;
+        if (j >= NB || (cx.vlo[j] - qx) >= thr) more = false;
+        else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); ++j; }
       }
-#pragma unroll 1
-      for (int s = lo; s < pl; ++s) {
-        const double yv = sy[s];
-        if (!((yv - qy) < thr)) break;
-        const double xv = sx[s];
-        ++np;
-        if (fabs(qx - xv) < thr && fabs(qy - yv) < thr) {
-          const int rel = p0 + s - own_rel;
-          if (rel < -kSeed || rel > kSeed) {
-            topk_insert<K1T>(best, fmax(fabs(qx - xv), fabs(qy - yv)));
-            thr = best[K1T - 1];
+      scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np);
+    }
+    if (more) {
+      while (j < NB && cx.count[j] == 0) ++j;
+      if (j < NB && !((cx.vlo[j] - qx) >= thr)) rstart = j;
+    }
+  }
+  {
+    bool more = valid;
+    int j = b - 1;
+    for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
+      int a = 0, e = 0;
+      if (more) {
+        int lj = 0;
+        while (j >= 0 && (lj = cx.count[j]) == 0) --j;
+        if (j < 0 || (qx - cx.vhi[j]) >= thr) more = false;
+        else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); --j; }
+      }
+      scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np);
+    }
+    if (more) {
+      while (j >= 0 && cx.count[j] == 0) --j;
+      if (j >= 0 && !((qx - cx.vhi[j]) >= thr)) lend = j + 1;
+    }
+  }
+  // ---- hand the rest to the leftover kernel: one reservation per warp
+  const bool want = valid && (rstart < NB || lend > 0);
+  const unsigned m = __ballot_sync(kFull, want);
+  int my_e = -1;
+  if (m != 0) {
+    const int leader = __ffs(m) - 1;
+    unsigned base_e = 0;
+    if (lane == leader) base_e = atomicAdd(pr.left_count, (unsigned)__popc(m));
+    base_e = __shfl_sync(kFull, base_e, leader);
+    if (base_e + __popc(m) <= left_cap) {
+      if (want) my_e = (int)(base_e + __popc(m & ((1u << lane) - 1u)));
+    } else {
+      // rare (the list is full): finish both directions here, one bucket and one slot at a time
+      if (lane == leader) atomicSub(pr.left_count, (unsigned)__popc(m));
+      if (want) {
+        for (int jj = rstart; jj < NB; ++jj) {
+          const int lj = cx.count[jj];
+          if (lj == 0) continue;
+          if ((cx.vlo[jj] - qx) >= thr) break;
+          int a, e;
+          bucket_window(pr, cx.boff[jj], lj, pr.bymin[jj], pr.bysc[jj], qy, thr, a, e);
+          for (int s = a; s < e; ++s) {
+            const double xh = px[s], yh = py[s];
+            if (fabs(qx - xh) < thr && fabs(qy - yh) < thr) { topk_insert<K1T>(best, fmax(fabs(qx - xh), fabs(qy - yh))); thr = best[K1T - 1]; }
+          }
+        }
+        for (int jj = lend - 1; jj >= 0; --jj) {
+          const int lj = cx.count[jj];
+          if (lj == 0) continue;
+          if ((qx - cx.vhi[jj]) >= thr) break;
+          int a, e;
+          bucket_window(pr, cx.boff[jj], lj, pr.bymin[jj], pr.bysc[jj], qy, thr, a, e);
+          for (int s = a; s < e; ++s) {
+            const double xh = px[s], yh = py[s];
+            if (fabs(qx - xh) < thr && fabs(qy - yh) < thr) { topk_insert<K1T>(best, fmax(fabs(qx - xh), fabs(qy - yh))); thr = best[K1T - 1]; }
           }
         }
       }
     }
-    __syncwarp();
-  }
-}
-
-// ---- knn: one warp = 32 y-neighbours of one chunk --------------------------------------------------------------------
-template <int K1T>
-__global__ void __launch_bounds__(kWarps * 32) knn_kernel2(const Col* cols, const Prob* probs, int B, int k, int defer_below,
-                                                           int near, unsigned left_cap, const Shard sh) {
-  __shared__ int s_soff[kMaxBuckets + 1];
-  __shared__ __align__(16) double s_stage[kWarps][2][kPiece];
-  const Prob pr = probs[blockIdx.y];
-  const Col cx = cols[pr.cx], cy = cols[pr.cy];
-  if ((*cx.flag | *cy.flag) != 0) return;
-  for (int b = threadIdx.x; b <= B; b += blockDim.x) s_soff[b] = cx.soff[b];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int total = s_soff[B];
-  const int nblocks = (total + kBlockSlots - 1) / kBlockSlots;
-  int blo, bhi;
-  shard_blocks(sh, nblocks, blo, bhi);
-  // work items: the first and last two warps of every chunk first (they sit in the sparse ends of y and search the
-  // widest windows), then everything else in slot order
-  const int item = blockIdx.x * kWarps + warp;
-  int c, wi;
-  if (item < 4 * B) {
-    c = item >> 2;
-    const int e = item & 3;
-    const int nw = (s_soff[c + 1] - s_soff[c]) >> 5;
-    wi = e < 2 ? e : nw - 1 - (e - 2);
-    if (e < 2 ? (e >= nw) : (wi < 2)) return;
-  } else {
-    const int g = item - 4 * B;
-    if (g >= (total >> 5)) return;
-    const int s0 = g << 5;
-    int lo = 0, hi = B;              // last chunk whose first slot is <= s0 (empty chunks share a first slot: take the last)
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_soff[mid] <= s0) lo = mid; else hi = mid - 1;
-    }
-    c = lo;
-    const int nw = (s_soff[c + 1] - s_soff[c]) >> 5;
-    wi = (s0 - s_soff[c]) >> 5;
-    if (wi < 2 || wi >= nw - 2) return;
-  }
-  const int base = s_soff[c];
-  const int own = wi * 32 + lane;              // chunk-relative slot of this lane's query
-  const int slot = base + own;
-  if (slot < blo * kBlockSlots || slot >= bhi * kBlockSlots) return;     // (uniform over the warp: 32 | kBlockSlots)
-  const int len_home = cx.count[c];
-  const bool valid = own < len_home;
-  const double qx = pr.px[slot], qy = pr.py[slot];      // NaN in padding slots: every test fails
-  const double kInf = d_inf();
-  double best[K1T];
-#pragma unroll
-  for (int t = 0; t < K1T; ++t) best[t] = kInf;
-  double thr = kInf;
-  unsigned long long np = 0;
-  double* sx = s_stage[warp][0];
-  double* sy = s_stage[warp][1];
-
-  // 1. seed the list from the query's own neighbourhood in y (coalesced: lane l reads slot own + o)
-#pragma unroll 1
-  for (int o = -kSeed; o <= kSeed; ++o) {
-    const int s = own + o;
-    if (s >= 0 && s < len_home) {
-      const double xv = pr.px[base + s], yv = pr.py[base + s];
-      if (fabs(qx - xv) < thr && fabs(qy - yv) < thr) {
-        topk_insert<K1T>(best, fmax(fabs(qx - xv), fabs(qy - yv)));
-        thr = best[K1T - 1];
-      }
-    }
-  }
-  np += 2 * kSeed + 1;
-
-  // 2. the rest of the home chunk
-  scan_chunk<K1T>(cx.count[c], pr.px + base, pr.py + base, valid, own, qx, qy, best, thr, np, sx, sy, lane);
-  // 3. outwards over the chunks: a query needs chunk j only while the gap to the chunk's x range is below its
-  //    current k-th distance (rounded subtraction is monotone => exact)
-  int rstart = B, lend = 0;
-  int my_e = -1;                 // this lane's entry in the deferral list, once reserved
-  bool may_defer = defer_below > 0;
-  // the lanes of `m` hand the rest of a direction to the leftover kernel: entries are reserved here (the list has
-  // room for left_cap of them; when it is full the warp simply keeps searching)
-  auto reserve = [&](unsigned m) -> bool {
-    const unsigned fresh = __ballot_sync(kFull, ((m >> lane) & 1u) && my_e < 0);
-    if (fresh == 0) return true;
-    unsigned base_e = 0;
-    if (lane == 0) base_e = atomicAdd(pr.left_count, (unsigned)__popc(fresh));
-    base_e = __shfl_sync(kFull, base_e, 0);
-    if (base_e + __popc(fresh) > left_cap) {
-      if (lane == 0) atomicSub(pr.left_count, (unsigned)__popc(fresh));
-      return false;
-    }
-    if ((fresh >> lane) & 1u) my_e = (int)(base_e + __popc(fresh & ((1u << lane) - 1u)));
-    return true;
-  };
-  for (int j = c + 1; j < B; ++j) {
-    const double cmin = cx.lo[j];
-    const bool need = valid && !((cmin - qx) >= thr);
-    const unsigned m = __ballot_sync(kFull, need);
-    if (m == 0) break;
-    if (may_defer && j - c > near && __popc(m) < defer_below) {
-      if (reserve(m)) {
-        if (need) rstart = j;
-        break;
-      }
-      may_defer = false;
-    }
-    scan_chunk<K1T>(cx.count[j], pr.px + s_soff[j], pr.py + s_soff[j], need, -(1 << 28), qx, qy, best, thr, np, sx, sy, lane);
-  }
-  for (int j = c - 1; j >= 0; --j) {
-    const double cmax = cx.hi[j];
-    const bool need = valid && !((qx - cmax) >= thr);
-    const unsigned m = __ballot_sync(kFull, need);
-    if (m == 0) break;
-    if (may_defer && c - j > near && __popc(m) < defer_below) {
-      if (reserve(m)) {
-        if (need) lend = j + 1;
-        break;
-      }
-      may_defer = false;
-    }
-    scan_chunk<K1T>(cx.count[j], pr.px + s_soff[j], pr.py + s_soff[j], need, -(1 << 28), qx, qy, best, thr, np, sx, sy, lane);
   }
   if (valid) {
     double r = best[0];
@@ -483,12 +640,11 @@ __global__ void __launch_bounds__(kWarps * 32) knn_kernel2(const Col* cols, cons
     for (int t = 1; t < K1T; ++t) r = (t <= k) ? best[t] : r;       // = best[k] (a chain of selects, no indexed access)
     pr.eps[slot] = r;
     if (my_e >= 0) {
-      const unsigned e = (unsigned)my_e;
       LeftEnt le;
       le.slot = slot; le.rstart = rstart; le.lend = lend;
-      pr.left[e] = le;
+      pr.left[my_e] = le;
 #pragma unroll
-      for (int t = 0; t < K1T; ++t) pr.left_best[(long long)e * K1T + t] = best[t];
+      for (int t = 0; t < K1T; ++t) pr.left_best[(long long)my_e * K1T + t] = best[t];
     }
   }
 #pragma unroll
@@ -496,10 +652,11 @@ __global__ void __launch_bounds__(kWarps * 32) knn_kernel2(const Col* cols, cons
   if (lane == 0 && np) atomicAdd(reinterpret_cast<unsigned long long*>(pr.out + 4), np);
 }
 
-// ---- leftover: one warp finishes one deferred query ------------------------------------------------------------------
+// ---- leftover: one warp finishes one deferred query, its remaining buckets dealt to the lanes ------------------------
 template <int K1T>
-__global__ void __launch_bounds__(kWarps * 32) leftover_kernel2(const Col* cols, const Prob* probs, int B, int k, long long n,
-                                                                int ypath_min_chunks, int ypath_cost) {
+__global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, const Prob* probs, int NB, int k) {
+  __shared__ int s_hit[kHitCap * kThreadsB];
+  int* hit = s_hit + threadIdx.x;
   const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
@@ -508,7 +665,7 @@ __global__ void __launch_bounds__(kWarps * 32) leftover_kernel2(const Col* cols,
   const double kInf = d_inf();
   const int k1 = k + 1;
   unsigned long long np = 0;
-  for (unsigned e = blockIdx.x * kWarps + warp; e < nent; e += gridDim.x * kWarps) {
+  for (unsigned e = blockIdx.x * (kThreadsB / 32) + warp; e < nent; e += gridDim.x * (kThreadsB / 32)) {
     const LeftEnt le = pr.left[e];
     const double qx = pr.px[le.slot], qy = pr.py[le.slot];
     const double gate = pr.left_best[(long long)e * K1T + (K1T - 1)];      // current k-th distance: upper bound of eps
@@ -516,66 +673,23 @@ __global__ void __launch_bounds__(kWarps * 32) leftover_kernel2(const Col* cols,
 #pragma unroll
     for (int t = 0; t < K1T; ++t) best[t] = kInf;
     double thr = gate;
-    // chunks that can still hold a neighbour: gap in x below the gate (monotone => exact)
-    int r_lo = B, r_hi = B, l_lo = 0, l_hi = 0;
-    if (le.rstart < B) {
-      r_lo = le.rstart;
-      r_hi = warp_first_true(r_lo, B, [&](int j) { return (cx.lo[j] - qx) >= gate; });
-    }
-    if (le.lend > 0) {
-      l_hi = le.lend;
-      l_lo = warp_first_true(0, l_hi, [&](int j) { return !((qx - cx.hi[j]) >= gate); });
-    }
-    const int nr = r_hi - r_lo, nl = l_hi - l_lo;
-    const double lo_v = (qy - gate) - (fabs(qy) + gate) * kSlack;
-    const double hi_v = (qy + gate) + (fabs(qy) + gate) * kSlack;
-    bool by_y = false;
-    int ya = 0, yb = 0;
-    if (nr + nl >= ypath_min_chunks && gate < kInf) {
-      // a query in a sparse region of y: the rows inside its y window are few - take them from the y-sorted column
-      // instead of searching a window in each of many chunks
-      ya = warp_first_true(0, (int)n, [&](int t) { return !(cy.sorted[t] < lo_v); });
-      yb = warp_first_true(ya, (int)n, [&](int t) { return cy.sorted[t] > hi_v; });
-      by_y = (long long)(yb - ya) < (long long)(nr + nl) * ypath_cost;
-    }
-    if (by_y) {
-      for (int t = ya + lane; t < yb; t += 32) {
-        const int row = cy.perm[t];
-        const int cb = cx.bid[row];
-        if (cb >= le.lend && cb < le.rstart) continue;        // chunks the search kernel has already examined
-        const double yv = cy.sorted[t], xv = cx.vals[row];
-        const double m = fmax(fabs(qx - xv), fabs(qy - yv));
-        if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
+    for (int j0 = le.rstart; j0 < NB; j0 += 32) {
+      const int j = j0 + lane;
+      const int len = j < NB ? cx.count[j] : 0;
+      const bool fail = len > 0 && (cx.vlo[j] - qx) >= gate;               // monotone: every bucket further right fails too
+      if (len > 0 && !fail) {
+        visit_bucket<K1T, true>(pr, cx.boff[j], len, pr.bymin[j], pr.bysc[j], qx, qy, best, thr, np, 0, 0, gate, hit);
       }
-      if (lane == 0) np += (unsigned long long)(yb - ya);
-    } else {
-      // batches of 32 chunks: every lane binary-searches the y window of ITS chunk (the searches overlap their L2
-      // latency), then the warp walks the non-empty windows together
-      for (int b0 = 0; b0 < nr + nl; b0 += 32) {
-        const int idx = b0 + lane;
-        int wlo = 0, whi = 0, cbase = 0;
-        if (idx < nr + nl) {
-          const int ch = idx < nr ? r_lo + idx : l_lo + (idx - nr);
-          cbase = cx.soff[ch];
-          const int lenv = cx.count[ch];
-          const double* yrow = pr.py + cbase;
-          wlo = lower_bound_ge(yrow, lenv, lo_v);
-          whi = upper_bound_gt(yrow, lenv, hi_v);
-        }
-        unsigned todo = __ballot_sync(kFull, wlo < whi);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int slo = __shfl_sync(kFull, wlo, src), shi = __shfl_sync(kFull, whi, src);
-          const int sbase = __shfl_sync(kFull, cbase, src);
-          for (int j = slo + lane; j < shi; j += 32) {
-            const double xv = pr.px[sbase + j], yv = pr.py[sbase + j];
-            const double m = fmax(fabs(qx - xv), fabs(qy - yv));
-            if (m < thr) { topk_insert<K1T>(best, m); thr = fmin(best[K1T - 1], gate); }
-          }
-          if (lane == 0) np += (unsigned long long)(shi - slo);
-        }
+      if (__any_sync(kFull, fail || j >= NB)) break;
+    }
+    for (int j0 = le.lend - 1; j0 >= 0; j0 -= 32) {
+      const int j = j0 - lane;
+      const int len = j >= 0 ? cx.count[j] : 0;
+      const bool fail = len > 0 && (qx - cx.vhi[j]) >= gate;
+      if (len > 0 && !fail) {
+        visit_bucket<K1T, true>(pr, cx.boff[j], len, pr.bymin[j], pr.bysc[j], qx, qy, best, thr, np, 0, 0, gate, hit);
       }
+      if (__any_sync(kFull, fail || j < 0)) break;
     }
     // the list the search kernel left behind joins lane 0's (disjoint candidates), then one merge across the lanes
     if (lane == 0) {
@@ -588,105 +702,140 @@ __global__ void __launch_bounds__(kWarps * 32) leftover_kernel2(const Col* cols,
     const double fin = warp_merge_lists<K1T>(best, k1);
     if (lane == k) pr.eps[le.slot] = fin;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_down_sync(kFull, np, o);
   if (lane == 0 && np) atomicAdd(reinterpret_cast<unsigned long long*>(pr.out + 4), np);
 }
 
-// ---- marginal counts + digamma terms, per 256-slot block -------------------------------------------------------------
+// ---- marginal counts + digamma terms -------------------------------------------------------------------------------------
+struct GridView {           // a column's fine grid; the bucket function's tables live in shared memory
+  BucketFn fn;
+  const FineGrid* fg;
+  const double* fval;
+  const int* fstart;
+};
+
+// quantile stretch of t, found by walking from a stretch nearby (the query's own): the unique c with
+// split[c - 1] < t <= split[c], i.e. the number of splitters below t, as the binary search of bucket_fn gives
+__device__ __forceinline__ int stretch_near(const BucketFn& f, int c, double t) {
+  while (c > 0 && !(f.split[c - 1] < t)) --c;
+  while (c < f.Bc - 1 && f.split[c] < t) ++c;
+  return c;
+}
+
+// index of the fine cell a threshold t falls into (monotone non-decreasing in t); an empty bucket has no cells of its
+// own and yields the first cell of the next bucket.  c: a stretch near t (updated to t's own).
+__device__ __forceinline__ int cell_index(const GridView& g, int& c, double t) {
+  c = stretch_near(g.fn, c, t);
+  const int b = c * kSub + lin_cell(t, g.fn.clo[c], g.fn.csc[c], kSub);
+  const FineGrid fg = g.fg[b];
+  return fg.ncell == 0 ? fg.boff : fg.boff + lin_cell(t, fg.vlo, fg.fsc, fg.ncell);
+}
+
+// #{j : |fl(v - s_j)| <= r} over the whole column (the point itself included): cells strictly between the boundary
+// cells of the two thresholds are inside whatever their values (the thresholds are widened by more than the rounding
+// of the subtraction), values in boundary cells are tested exactly.  c0: the quantile stretch of v.
+__device__ __forceinline__ int grid_count(const GridView& g, int c0, double v, double r) {
+  if (!(r >= 0.0)) return 0;
+  const double w = (fabs(v) + r) * kSlack;
+  int c = c0;
+  const int i2 = cell_index(g, c, (v - r) + w);
+  const int i1 = cell_index(g, c, (v - r) - w);
+  c = c0;
+  const int i3 = cell_index(g, c, (v + r) - w);
+  const int i4 = cell_index(g, c, (v + r) + w);
+  int cnt = 0;
+  const int a1 = g.fstart[i1], e1 = g.fstart[i2 + 1];
+  const int i3b = max(i3, i2 + 1);
+  const int a2 = i4 >= i3b ? g.fstart[i3b] : 0, e2 = i4 >= i3b ? g.fstart[i4 + 1] : 0;
+  for (int s = a1; s < e1; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
+  if (i3b > i2 + 1) cnt += a2 - e1;                        // whole cells between the boundaries
+  for (int s = a2; s < e2; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
+  return cnt;
+}
+
 __device__ __forceinline__ double psi_lookup(const double* tab, int tab_n, int c) { return c < tab_n ? tab[c] : psi_ref((double)c); }
 
-__global__ void __launch_bounds__(kBlockSlots) count_psi_kernel(const Col* cols, const Prob* probs, int B, long long n, int nblk,
-                                                                 const Shard sh, const double* psi_tab, int tab_n) {
-  __shared__ double red[kBlockSlots / 32];
-  const Prob pr = probs[blockIdx.z];
+__global__ void __launch_bounds__(kThreadsB) count_psi_kernel(const Col* cols, const Prob* probs, long long n, int Bc,
+                                                               const Shard sh, const double* psi_tab, int tab_n) {
+  __shared__ double s_tab[2][3][kMaxCoarse];
+  __shared__ long long s_red[kThreadsB / 32];
+  __shared__ int s_redi[3][kThreadsB / 32];
+  const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
-  const int which = blockIdx.y;                      // 0: n_x in the sorted x, 1: n_y in the sorted y
-  const int total = cx.soff[B];
-  const int nblocks = (total + kBlockSlots - 1) / kBlockSlots;
-  int blo, bhi;
-  shard_blocks(sh, nblocks, blo, bhi);
-  const int blk = blockIdx.x;
-  if (blk < blo || blk >= bhi) return;
-  const int slot = blk * kBlockSlots + threadIdx.x;
-  const int row = slot < total ? pr.slot_row[slot] : -1;
-  const bool act = row >= 0;
-  const double* s = which ? cy.sorted : cx.sorted;
-  const double x = act ? (which ? pr.py[slot] : pr.px[slot]) : 0.0;
-  const double e = act ? pr.eps[slot] : 0.0;
-  const double r = act ? e - 1e-12 : 0.0;            // _entropy_estimators.py:109
-  const int len = (int)n;
-  const double kInf = d_inf();
-  // the queries of a warp are neighbours in the layout: two warp-uniform 33-way searches bracket the stretch of the
-  // sorted column their answers lie in (widened by 2^-50 relative), the exact per-lane searches run inside it
-  double xmin = warp_min(act ? x : kInf), xmax = warp_max(act ? x : -kInf), rmax = warp_max(act ? fmax(r, 0.0) : 0.0);
-  int wl = 0, wh = len;
-  if (xmin <= xmax) {
-    const double lo_v = (xmin - rmax) - (fabs(xmin) + rmax) * kSlack;
-    const double hi_v = (xmax + rmax) + (fabs(xmax) + rmax) * kSlack;
-    wl = warp_first_true(0, len, [&](int j) { return !(s[j] < lo_v); });
-    wh = warp_first_true(wl, len, [&](int j) { return s[j] > hi_v; });
+  for (int q = threadIdx.x; q < Bc; q += blockDim.x) {
+    s_tab[0][0][q] = q < Bc - 1 ? cx.split[q] : d_inf(); s_tab[0][1][q] = cx.clo[q]; s_tab[0][2][q] = cx.csc[q];
+    s_tab[1][0][q] = q < Bc - 1 ? cy.split[q] : d_inf(); s_tab[1][1][q] = cy.clo[q]; s_tab[1][2][q] = cy.csc[q];
   }
-  int cnt = 0;
+  __syncthreads();
+  const GridView gx{{s_tab[0][0], s_tab[0][1], s_tab[0][2], Bc}, cx.fg, cx.fval, cx.fstart};
+  const GridView gy{{s_tab[1][0], s_tab[1][1], s_tab[1][2], Bc}, cy.fg, cy.fval, cy.fstart};
+  const long long s64 = (long long)blockIdx.x * kThreadsB + threadIdx.x;
+  const int slot = (int)min(s64, n - 1);
+  const int off = cx.boff[pr.pbkt[slot]];
+  const bool act = s64 < n && off >= sh.row_lo && off < sh.row_hi;
+  long long q = 0;
+  int zx = 0, zy = 0;
   if (act) {
-    // lower bound: first j with fl(x - s_j) <= r (non-increasing in j); upper bound: first j with fl(s_j - x) > r
-    int first = wl, fhi = wh, lo = wl, hi = wh;
-    while (first < fhi || lo < hi) {
-      const int m1 = (first + fhi) >> 1, m2 = (lo + hi) >> 1;
-      const double v1 = s[min(m1, len - 1)], v2 = s[min(m2, len - 1)];
-      if (first < fhi) { if ((x - v1) <= r) fhi = m1; else first = m1 + 1; }
-      if (lo < hi) { if ((v2 - x) > r) hi = m2; else lo = m2 + 1; }
-    }
-    cnt = max(0, lo - first);
-    if (which == 0) {
-      if (pr.nx_row) pr.nx_row[row] = cnt;
-      if (pr.eps_row) pr.eps_row[row] = e;
-    } else if (pr.ny_row) {
-      pr.ny_row[row] = cnt;
-    }
+    const double e = pr.eps[slot];
+    const double r = e - 1e-12;                                // _entropy_estimators.py:109
+    const int row = pr.prow[slot];
+    const int nx = grid_count(gx, pr.pbkt[slot] / kSub, pr.px[slot], r);
+    const int ny = grid_count(gy, cy.bkt[row] / kSub, pr.py[slot], r);
+    if (pr.eps_row) pr.eps_row[row] = e;
+    if (pr.nx_row) pr.nx_row[row] = nx;
+    if (pr.ny_row) pr.ny_row[row] = ny;
+    // a zero count makes the reference's _psi return a scalar +inf (:338-339): reported through the zero counters
+    double term = 0.0;
+    if (nx == 0) zx = 1; else term = psi_lookup(psi_tab, tab_n, nx);
+    if (ny == 0) zy = 1; else term = term + psi_lookup(psi_tab, tab_n, ny);
+    q = __double2ll_rn(term * 281474976710656.0);             // units of 2^-48: |term| < 32, so |q| < 2^53
   }
-  double term = 0.0, zero = 0.0;
-  if (act) {
-    if (cnt == 0) zero = 1.0; else term = psi_lookup(psi_tab, tab_n, cnt);
+  int na = act ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q += __shfl_down_sync(kFull, q, o);
+    zx += __shfl_down_sync(kFull, zx, o);
+    zy += __shfl_down_sync(kFull, zy, o);
+    na += __shfl_down_sync(kFull, na, o);
   }
-  const int nact = __syncthreads_count(act);
-  term = block_sum<kBlockSlots>(term, red);
-  zero = block_sum<kBlockSlots>(zero, red);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_red[w] = q; s_redi[0][w] = zx; s_redi[1][w] = zy; s_redi[2][w] = na; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double* p = pr.partial + ((long long)which * nblk + blk) * 2;
-    p[0] = term;
-    p[1] = zero;
-    if (which == 0 && nact) atomicAdd(reinterpret_cast<unsigned long long*>(pr.out + 6), (unsigned long long)nact);   // rows reduced
+    long long tq = 0;
+    int tzx = 0, tzy = 0, tna = 0;
+    for (int i = 0; i < kThreadsB / 32; ++i) { tq += s_red[i]; tzx += s_redi[0][i]; tzy += s_redi[1][i]; tna += s_redi[2][i]; }
+    if (tna) {
+      // 128-bit signed accumulation in two words: integer addition is associative, the total is order-free
+      const unsigned long long add_lo = (unsigned long long)tq;
+      const unsigned long long old = atomicAdd(&pr.acc[0], add_lo);
+      const unsigned long long carry = (old + add_lo < old) ? 1ull : 0ull;
+      const unsigned long long add_hi = (tq < 0 ? ~0ull : 0ull) + carry;
+      if (add_hi) atomicAdd(&pr.acc[1], add_hi);
+      if (tzx) atomicAdd(&pr.acc[2], (unsigned long long)tzx);
+      if (tzy) atomicAdd(&pr.acc[3], (unsigned long long)tzy);
+      atomicAdd(reinterpret_cast<unsigned long long*>(pr.out + 6), (unsigned long long)tna);     // rows reduced
+    }
   }
 }
 
-// ---- fixed-order fold of the block partials ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) final_kernel(const Col* cols, const Prob* probs, int B, int nblk) {
-  __shared__ double red[8];
+__global__ void final_kernel(const Col* cols, const Prob* probs) {
   const Prob pr = probs[blockIdx.x];
-  const Col cx = cols[pr.cx], cy = cols[pr.cy];
-  const int fl = *cx.flag | *cy.flag;
-  int* oflag = reinterpret_cast<int*>(pr.out + 5);
+  const int fl = *cols[pr.cx].flag | *cols[pr.cy].flag;
   if (fl != 0) {
-    if (threadIdx.x == 0) atomicOr(oflag, fl);
+    atomicOr(reinterpret_cast<int*>(pr.out + 5), fl);
     return;
   }
-  const int total = cx.soff[B];
-  const int nblocks = (total + kBlockSlots - 1) / kBlockSlots;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};          // psi(n_x) sum, zeros_x, psi(n_y) sum, zeros_y
-  for (int b = threadIdx.x; b < nblocks; b += 256) {
-    const double* px = pr.partial + (long long)b * 2;
-    const double* py = pr.partial + ((long long)nblk + b) * 2;
-    acc[0] += px[0]; acc[1] += px[1]; acc[2] += py[0]; acc[3] += py[1];
-  }
-  double out[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) out[c] = block_sum<256>(acc[c], red);
-  if (threadIdx.x == 0) {
-    pr.out[0] = out[0] + out[2];
-    pr.out[1] = out[1];
-    pr.out[2] = out[3];
-    pr.out[3] = 0.0;
-  }
+  const unsigned long long lo = pr.acc[0];
+  const long long hi = (long long)pr.acc[1];
+  pr.out[0] = ((double)hi * 18446744073709551616.0 + (double)lo) * (1.0 / 281474976710656.0);   // informative; the host
+  pr.out[1] = (double)pr.acc[2];                                                                // uses the exact words
+  pr.out[2] = (double)pr.acc[3];
+  pr.out[3] = 0.0;
+  reinterpret_cast<unsigned long long*>(pr.out)[8] = lo;
+  reinterpret_cast<long long*>(pr.out)[9] = hi;
 }
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -696,34 +845,39 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 Plan make_plan(int64_t n, bool* ok) {
   Plan p;
   p.n = n;
-  int64_t B = (n + kBucketMean - 1) / kBucketMean;
-  if (B < 1) B = 1;
+  // rows per bucket ~ 2 sqrt(n): a bucket should be about as wide in x as a typical k-th neighbour distance, which
+  // shrinks like 1 / sqrt(n) in two dimensions
+  int64_t rows = 256;
+  while (rows < kCoarseRows && rows * rows < 4 * n) rows += 64;
+  int64_t Bc = (n + rows - 1) / rows;
+  if (Bc < 1) Bc = 1;
   bool fits = n >= 2 && n < (int64_t(1) << 30);
-  if (B > kMaxBuckets) {
-    B = kMaxBuckets;
-    if (n > int64_t(kMaxBuckets) * (kBucketMean + kBucketMean / 4)) fits = false;     // buckets would run too full
+  if (Bc > kMaxCoarse) {
+    Bc = kMaxCoarse;
+    if (n > int64_t(kMaxCoarse) * (kCoarseRows + kCoarseRows / 2)) fits = false;     // buckets would run too full
   }
-  p.B = static_cast<int>(B);
-  int64_t over = n / B;
+  p.Bc = static_cast<int>(Bc);
+  p.NB = p.Bc * kSub;
+  int64_t over = n / Bc;
   if (over > kOversample) over = kOversample;
   if (over < 1) over = 1;
   p.over = static_cast<int>(over);
-  p.smax = (n + 32 * B + kBlockSlots - 1) / kBlockSlots * kBlockSlots;
-  p.nblk = static_cast<int>(p.smax / kBlockSlots);
   if (ok) *ok = fits;
   return p;
 }
 
 size_t col_bytes(int64_t n) {
   size_t b = 0;
-  b += align256(sizeof(double) * n);                 // sorted
-  b += align256(sizeof(int) * n);                    // perm
-  b += align256(sizeof(unsigned short) * n);         // bid
-  b += align256(sizeof(double) * n);                 // st_val
-  b += align256(sizeof(int) * n);                    // st_row
-  b += align256(sizeof(double) * kMaxBuckets) * 3;   // split, lo, hi
-  b += align256(sizeof(int) * (kMaxBuckets + 1)) * 4;  // count, fill, boff, soff
-  b += 256;                                          // flag
+  b += align256(sizeof(double) * kMaxCoarse) * 3;            // split, clo, csc
+  b += align256(sizeof(double) * kMaxCoarse * kOversample) * 2;  // ssort, sraw
+  b += align256(sizeof(int) * (kMaxBuckets + 1)) * 4;        // count, fill, boff, ncell
+  b += align256(sizeof(double) * kMaxBuckets) * 3;           // vlo, vhi, fsc
+  b += align256(sizeof(FineGrid) * kMaxBuckets);             // fg
+  b += align256(sizeof(unsigned short) * n);                 // bkt
+  b += align256(sizeof(int) * n);                            // srow
+  b += align256(sizeof(double) * n) * 2;                     // sval, fval
+  b += align256(sizeof(int) * (n + 2));                      // fstart
+  b += 256;                                                  // flag
   return b;
 }
 
@@ -732,34 +886,41 @@ Col carve_col(char* base, int64_t n, const double* vals) {
   size_t o = 0;
   auto take = [&](size_t bytes) { char* p = base + o; o += align256(bytes); return p; };
   c.vals = vals;
-  c.sorted = reinterpret_cast<double*>(take(sizeof(double) * n));
-  c.perm = reinterpret_cast<int*>(take(sizeof(int) * n));
-  c.bid = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * n));
-  c.st_val = reinterpret_cast<double*>(take(sizeof(double) * n));
-  c.st_row = reinterpret_cast<int*>(take(sizeof(int) * n));
-  c.split = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
-  c.lo = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
-  c.hi = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  c.split = reinterpret_cast<double*>(take(sizeof(double) * kMaxCoarse));
+  c.clo = reinterpret_cast<double*>(take(sizeof(double) * kMaxCoarse));
+  c.csc = reinterpret_cast<double*>(take(sizeof(double) * kMaxCoarse));
+  c.ssort = reinterpret_cast<double*>(take(sizeof(double) * kMaxCoarse * kOversample));
+  c.sraw = reinterpret_cast<double*>(take(sizeof(double) * kMaxCoarse * kOversample));
   c.count = reinterpret_cast<int*>(take(sizeof(int) * (kMaxBuckets + 1)));
   c.fill = reinterpret_cast<int*>(take(sizeof(int) * (kMaxBuckets + 1)));
   c.boff = reinterpret_cast<int*>(take(sizeof(int) * (kMaxBuckets + 1)));
-  c.soff = reinterpret_cast<int*>(take(sizeof(int) * (kMaxBuckets + 1)));
+  c.ncell = reinterpret_cast<int*>(take(sizeof(int) * (kMaxBuckets + 1)));
+  c.vlo = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  c.vhi = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  c.fsc = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  c.fg = reinterpret_cast<FineGrid*>(take(sizeof(FineGrid) * kMaxBuckets));
+  c.bkt = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * n));
+  c.srow = reinterpret_cast<int*>(take(sizeof(int) * n));
+  c.sval = reinterpret_cast<double*>(take(sizeof(double) * n));
+  c.fval = reinterpret_cast<double*>(take(sizeof(double) * n));
+  c.fstart = reinterpret_cast<int*>(take(sizeof(int) * (n + 2)));
   c.flag = reinterpret_cast<int*>(take(sizeof(int)));
   return c;
 }
 
 // entries the deferral list of a problem can hold (a full list only means that the search kernel keeps going itself)
-size_t left_cap(const Plan& p) { return static_cast<size_t>(p.n / 8 + 1024); }
+static size_t left_cap(const Plan& p) { return static_cast<size_t>(p.n / 4 + 1024); }
 
 size_t prob_bytes(const Plan& p, int k1t) {
   size_t b = 0;
-  b += align256(sizeof(double) * p.smax) * 3;                 // px, py, eps
-  b += align256(sizeof(int) * p.smax);                        // slot_row
+  b += align256(sizeof(double) * p.n) * 3;                    // px, py, eps
+  b += align256(sizeof(int) * p.n);                           // prow
+  b += align256(sizeof(unsigned short) * p.n);                // pbkt
+  b += align256(sizeof(int) * (p.n + 2));                     // cstart
+  b += align256(sizeof(double) * kMaxBuckets) * 2;            // bymin, bysc
   b += align256(sizeof(LeftEnt) * left_cap(p));               // left
   b += align256(sizeof(double) * left_cap(p) * k1t);          // left_best
-  b += align256(sizeof(double) * 4 * p.nblk);                 // partial
-  b += 256;                                                   // left_count
-  b += 256;                                                   // out
+  b += 256 * 3;                                               // left_count, acc, out
   return b;
 }
 
@@ -768,64 +929,57 @@ Prob carve_prob(char* base, const Plan& p, int k1t, int cx, int cy) {
   size_t o = 0;
   auto take = [&](size_t bytes) { char* ptr = base + o; o += align256(bytes); return ptr; };
   q.cx = cx; q.cy = cy;
-  q.px = reinterpret_cast<double*>(take(sizeof(double) * p.smax));
-  q.py = reinterpret_cast<double*>(take(sizeof(double) * p.smax));
-  q.eps = reinterpret_cast<double*>(take(sizeof(double) * p.smax));
-  q.slot_row = reinterpret_cast<int*>(take(sizeof(int) * p.smax));
+  q.px = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  q.py = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  q.eps = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  q.prow = reinterpret_cast<int*>(take(sizeof(int) * p.n));
+  q.pbkt = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * p.n));
+  q.cstart = reinterpret_cast<int*>(take(sizeof(int) * (p.n + 2)));
+  q.bymin = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  q.bysc = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
   q.left = reinterpret_cast<LeftEnt*>(take(sizeof(LeftEnt) * left_cap(p)));
   q.left_best = reinterpret_cast<double*>(take(sizeof(double) * left_cap(p) * k1t));
-  q.partial = reinterpret_cast<double*>(take(sizeof(double) * 4 * p.nblk));
   q.left_count = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int)));
-  q.out = reinterpret_cast<double*>(take(sizeof(double) * 8));
+  q.acc = reinterpret_cast<unsigned long long*>(take(sizeof(unsigned long long) * 4));
+  q.out = reinterpret_cast<double*>(take(sizeof(double) * 16));
   q.eps_row = nullptr; q.nx_row = nullptr; q.ny_row = nullptr;
   return q;
 }
 
-namespace {
-constexpr size_t kSplitSmem = sizeof(double) * (kSplitThreads * kSplitItems + 1) + 64;
-constexpr size_t kSortSmem = sizeof(KV) * (kSortThreads * 8 + 1) + 64;
-}  // namespace
+cudaError_t init() { return cudaSuccess; }      // (no kernel needs an opt-in shared-memory size at present)
 
-cudaError_t init() {
-  cudaError_t e = cudaFuncSetAttribute(split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplitSmem);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
-}
-
-cudaError_t colsort(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
-  const int nb = static_cast<int>((p.n + kCountRows - 1) / kCountRows);
-  split_kernel<<<ncol, kSplitThreads, kSplitSmem, s>>>(cols, p.n, p.B, p.over);
-  bucket_count_kernel<<<dim3(nb, ncol), 256, 0, s>>>(cols, p.n, p.B);
-  bucket_scatter_kernel<<<dim3(nb, ncol), 256, 0, s>>>(cols, p.n, p.B);
-  bucket_sort_kernel<<<dim3(p.B, ncol), kSortThreads, kSortSmem, s>>>(cols, p.B);
-  if (launches) *launches += 4;
+cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
+  const int nb = static_cast<int>((p.n + kHistRows - 1) / kHistRows);
+  const int S = p.Bc * p.over;
+  sample_gather_kernel<<<dim3((S + kRankThreads - 1) / kRankThreads, ncol), kRankThreads, 0, s>>>(cols, p.n, S);
+  sample_rank_kernel<<<dim3((S + 31) / 32, ncol), kRankThreads, 0, s>>>(cols, S);
+  split_tables_kernel<<<ncol, kSplitThreads, 0, s>>>(cols, p.Bc, p.over, p.NB);
+  bucket_hist_kernel<<<dim3(nb, ncol), kThreadsB, 0, s>>>(cols, p.n, p.Bc, p.NB);
+  bucket_scatter_kernel<<<dim3(nb, ncol), kThreadsB, 0, s>>>(cols, p.n, p.NB);
+  fine_cells_kernel<<<dim3(p.NB, ncol), kThreadsB, 0, s>>>(cols, p.n, p.NB);
+  if (launches) *launches += 6;
   return cudaGetLastError();
 }
 
 cudaError_t layout(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches) {
-  layout_kernel<<<dim3(p.B, nprob), kSortThreads, kSortSmem, s>>>(cols, probs, p.B);
+  layout_kernel<<<dim3(p.NB, nprob), kLayoutThreads, 0, s>>>(cols, probs, p.n, p.NB);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
 
 cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, int k, const Shard& sh, int sm_count,
                 cudaStream_t s, int* launches) {
-  int defer_below = 8, near = 1, ymin = 8, ycost = 24;
-  if (const char* e = getenv("EB2_K2_DEFER")) defer_below = atoi(e);       // tuning knobs
-  if (const char* e = getenv("EB2_K2_NEAR")) near = atoi(e);
-  if (const char* e = getenv("EB2_K2_YMIN")) ymin = atoi(e);
-  if (const char* e = getenv("EB2_K2_YCOST")) ycost = atoi(e);
-  const int items = 4 * p.B + static_cast<int>(p.smax / 32);
-  const int grid = (items + kWarps - 1) / kWarps;
-  const int lgrid = nprob > 1 ? std::max(1, sm_count * 4 / nprob) : sm_count * 8;
+  int near = 2;
+  if (const char* e = getenv("EB2_K2_NEAR")) near = atoi(e);       // tuning knob: buckets per side before a query is deferred
+  const int grid = static_cast<int>((p.n + kThreadsB - 1) / kThreadsB);
+  const int lgrid = nprob > 1 ? std::max(1, sm_count * 8 / nprob) : sm_count * 8;
+  const unsigned cap = static_cast<unsigned>(left_cap(p));
   if (k + 1 <= 4) {
-    knn_kernel2<4><<<dim3(grid, nprob), kWarps * 32, 0, s>>>(cols, probs, p.B, k, defer_below, near, (unsigned)left_cap(p), sh);
-    leftover_kernel2<4><<<dim3(lgrid, nprob), kWarps * 32, 0, s>>>(cols, probs, p.B, k, p.n, ymin, ycost);
+    knn_kernel2<4><<<dim3(grid, nprob), kThreadsB, 0, s>>>(cols, probs, p.n, p.NB, k, near, cap, sh);
+    leftover_kernel2<4><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k);
   } else if (k + 1 <= 8) {
-    knn_kernel2<8><<<dim3(grid, nprob), kWarps * 32, 0, s>>>(cols, probs, p.B, k, defer_below, near, (unsigned)left_cap(p), sh);
-    leftover_kernel2<8><<<dim3(lgrid, nprob), kWarps * 32, 0, s>>>(cols, probs, p.B, k, p.n, ymin, ycost);
+    knn_kernel2<8><<<dim3(grid, nprob), kThreadsB, 0, s>>>(cols, probs, p.n, p.NB, k, near, cap, sh);
+    leftover_kernel2<8><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -835,13 +989,15 @@ cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, in
 
 cudaError_t count_psi(const Col* cols, const Prob* probs, int nprob, const Plan& p, const Shard& sh, const double* psi_tab,
                       int tab_n, cudaStream_t s, int* launches) {
-  count_psi_kernel<<<dim3(p.nblk, 2, nprob), kBlockSlots, 0, s>>>(cols, probs, p.B, p.n, p.nblk, sh, psi_tab, tab_n);
+  const int grid = static_cast<int>((p.n + kThreadsB - 1) / kThreadsB);
+  count_psi_kernel<<<dim3(grid, nprob), kThreadsB, 0, s>>>(cols, probs, p.n, p.Bc, sh, psi_tab, tab_n);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }
 
 cudaError_t finalize(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches) {
-  final_kernel<<<nprob, 256, 0, s>>>(cols, probs, p.B, p.nblk);
+  (void)p;
+  final_kernel<<<nprob, 1, 0, s>>>(cols, probs);
   if (launches) *launches += 1;
   return cudaGetLastError();
 }

@@ -1,23 +1,30 @@
-// ennemi_b200 — the bivariate KSG pipeline ("k2"): sample-sorted columns, bucket layout, warp-per-32-queries
-// neighbour search, fused marginal counts + digamma.  Host-side launch API; kernels in eb2_ksg2.cu.
+// ennemi_b200 — the bivariate KSG pipeline ("k2"): sort-free adaptive grid.  Host-side launch API; kernels in
+// eb2_ksg2.cu.
 //
 // One *column* is a prepared variable (n doubles in the caller's row order).  One *problem* is a pair of columns
 // (x, y) whose KSG estimate (_entropy_estimators.py:69-113) is wanted.  Every kernel takes arrays of columns /
-// problems and is launched once for all of them (blockIdx.y / .z = column / problem): a single estimate is a batch
-// of one, pairwise_mi a batch of hundreds of pairs that share 64 sorted columns.
+// problems and is launched once for all of them (blockIdx.y = column / problem): a single estimate is a batch of
+// one, pairwise_mi a batch of hundreds of pairs that share their columns.
 //
-// Per column (k2_colsort: four launches for any number of columns)
-//   splitters  B-1 values from a sorted regular sample (8 per bucket): bucket b holds split[b-1] < v <= split[b]
-//   sorted     the column in ascending order (bucket-major, every bucket sorted by one CTA in shared memory)
-//   perm       rank -> row;  bid: row -> bucket;  count / boff / soff: rows per bucket, first rank, first slot
-//   lo / hi    value range of every bucket
-// Per problem
-//   px, py, slot_row   the point set in SLOT order: the rows of x-bucket b ("chunk" b) occupy the slots
-//                      [soff[b], soff[b] + count[b]) in ascending y (ties by row), padded with NaN / -1 to a
-//                      multiple of 32 slots, so that a warp's 32 queries are 32 y-neighbours of one chunk
-//   eps                (k+1)-th neighbour distance per slot
-//   partial            per 256-slot block: sum of psi(n_x) [+ zero count], sum of psi(n_y) [+ zero count]
-//   out                4 doubles (sum, zeros_x, zeros_y, 0) + pair counter (u64) + flags (int) + rows reduced (u64 at [6])
+// Nothing is sorted.  A column is cut into BUCKETS by a monotone function of the value (sampled quantiles, each
+// quantile stretch cut linearly into kSub parts); the rows of a bucket are contiguous after one counting scatter.
+// Inside a bucket, values are grouped into CELLS by a second monotone (linear) function over the bucket's own
+// range, again by counting.  Because both functions are monotone and the SAME device function is used to build and
+// to query, "every value in a cell below cell(t) is below t" holds exactly, and the few values in boundary cells are
+// decided by the reference's exact predicates - counts and distances are bit-identical to an all-pairs evaluation.
+//
+// Per column (k2::colgrid: six launches for any number of columns)
+//   split / clo / csc   the bucket function;  bkt: row -> bucket;  count / boff: rows per bucket, first slot
+//   srow / sval         rows and values grouped by bucket
+//   fval / fstart       values grouped by (bucket, fine cell) and the first slot of every fine cell: what the marginal
+//                       neighbour counts (query_ball_point(..., return_length=True), :109-110) are read from
+// Per problem (x = column cx, y = column cy)
+//   px, py, prow, pbkt  the point set in SLOT order: the rows of x-bucket b occupy slots [boff[b], boff[b+1]), grouped
+//                       into cells of the bucket's own y range (about one row per cell); cstart: first slot per cell
+//   eps                 (k+1)-th neighbour distance per slot
+//   acc                 the digamma sum as a 128-bit fixed-point integer (2^-48 units) + zero-count counters: integer
+//                       addition is associative, so the sum does not depend on slot order, launch geometry or the
+//                       number of GPUs that shared the rows
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,11 +32,14 @@
 namespace eb2 {
 namespace k2 {
 
-constexpr int kBucketMean = 1024;    // target rows per bucket
-constexpr int kBucketCap = 4096;     // most rows one bucket may hold (one CTA sorts it in shared memory)
-constexpr int kMaxBuckets = 1024;
-constexpr int kOversample = 8;       // sample values per bucket the splitters are chosen from
-constexpr int kBlockSlots = 256;     // slots per reduction block (and per CTA of the count kernel)
+constexpr int kSub = 1;              // linear parts per quantile stretch (1: buckets are the quantile stretches themselves)
+constexpr int kMaxCoarse = 512;      // quantile stretches per column (at most)
+constexpr int kMaxBuckets = kSub * kMaxCoarse;
+constexpr int kCoarseRows = 2048;    // target rows per quantile stretch
+constexpr int kOversample = 8;       // sample values per quantile stretch
+constexpr int kBucketCap = 8192;     // most rows a bucket may hold (cells are built by one CTA in shared memory)
+constexpr int kMaxCells = 4096;      // most cells per bucket
+constexpr int kFixedBits = 48;       // digamma terms are accumulated in units of 2^-48
 
 // flag bits (columns and problems)
 constexpr int kFlagNaN = 1;          // NaN among the inputs of a prepared column (set by prep_kernel)
@@ -38,52 +48,65 @@ constexpr int kFlagOverflow = 16;    // a bucket outgrew kBucketCap: the caller 
 
 struct Plan {
   int64_t n = 0;
-  int B = 1;              // buckets per column
-  int over = 1;           // samples per bucket
-  int64_t smax = 0;       // upper bound of the slots of a problem (multiple of kBlockSlots)
-  int nblk = 0;           // smax / kBlockSlots
+  int Bc = 1;             // quantile stretches
+  int NB = kSub;          // buckets
+  int over = 1;           // samples per stretch
 };
-// n rows -> bucket count etc.; ok == false when the pipeline does not take this size
+// n rows -> grid sizes; ok == false when the pipeline does not take this size
 Plan make_plan(int64_t n, bool* ok);
+
+struct FineGrid {         // fine-cell map of one bucket, packed: one 32-byte load per threshold
+  double vlo, fsc;
+  int boff, ncell;
+};
 
 struct Col {
   const double* vals;     // [n] row order
-  double* sorted;         // [n]
-  int* perm;              // [n] rank -> row
-  unsigned short* bid;    // [n] row -> bucket
-  double* st_val;         // [n] scatter staging
-  int* st_row;            // [n]
-  double* split;          // [kMaxBuckets]
-  int* count;             // [kMaxBuckets]
-  int* fill;              // [kMaxBuckets]
-  int* boff;              // [kMaxBuckets + 1] first rank of bucket b
-  int* soff;              // [kMaxBuckets + 1] first slot of chunk b (multiples of 32); soff[B] = slots in use
-  double* lo;             // [kMaxBuckets]
-  double* hi;             // [kMaxBuckets]
+  double* split;          // [kMaxCoarse] upper ends of the quantile stretches (Bc - 1 used)
+  double* clo;            // [kMaxCoarse] lower end of the linear map of stretch c
+  double* csc;            // [kMaxCoarse] its scale (kSub / width, 0 for a degenerate stretch)
+  double* ssort;          // [kMaxCoarse * kOversample] the sample values in ascending order
+  double* sraw;           // [kMaxCoarse * kOversample] ... as gathered
+  int* count;             // [kMaxBuckets + 1]
+  int* fill;              // [kMaxBuckets + 1]
+  int* boff;              // [kMaxBuckets + 1] first slot of bucket b; boff[NB] = n
+  double* vlo;            // [kMaxBuckets] smallest value of the bucket (NaN: empty)
+  double* vhi;            // [kMaxBuckets] largest value
+  double* fsc;            // [kMaxBuckets] scale of the fine-cell map
+  int* ncell;             // [kMaxBuckets] fine cells of the bucket
+  FineGrid* fg;           // [kMaxBuckets] (vlo, fsc, boff, ncell) packed
+  unsigned short* bkt;    // [n] row -> bucket
+  int* srow;              // [n] rows grouped by bucket
+  double* sval;           // [n] their values
+  double* fval;           // [n] values grouped by (bucket, fine cell)
+  int* fstart;            // [n + 2] first slot of fine cell boff[b] + g; unused entries and the tail hold the next start
   int* flag;              // kFlag* bits of this column
 };
-// bytes of per-column scratch besides vals (everything a Col points to), for n rows
-size_t col_bytes(int64_t n);
-// carves a Col out of one allocation of col_bytes(n) bytes (256-byte aligned base)
-Col carve_col(char* base, int64_t n, const double* vals);
+size_t col_bytes(int64_t n);                                   // bytes of everything a Col points to besides vals
+Col carve_col(char* base, int64_t n, const double* vals);      // base: 256-byte aligned block of col_bytes(n) bytes
 
 struct LeftEnt {
   int slot;
-  int rstart;     // chunks [rstart, B) are still to be examined on the right (B: none)
-  int lend;       // chunks [0, lend) on the left (0: none)
+  int rstart;     // buckets [rstart, NB) are still to be examined on the right (NB: none)
+  int lend;       // buckets [0, lend) on the left (0: none)
 };
 
 struct Prob {
   int cx, cy;               // columns
-  double* px;               // [smax]
-  double* py;               // [smax]
-  int* slot_row;            // [smax]
-  double* eps;              // [smax]
+  double* px;               // [n]
+  double* py;               // [n]
+  int* prow;                // [n] slot -> row
+  unsigned short* pbkt;     // [n] slot -> x bucket
+  int* cstart;              // [n + 2] first slot of cell boff[b] + f
+  double* bymin;            // [kMaxBuckets] y-cell map of x-bucket b: cell = floor((y - bymin) * bysc)
+  double* bysc;             // [kMaxBuckets]
+  double* eps;              // [n] per slot
   LeftEnt* left;            // [left_cap]
   double* left_best;        // [left_cap][K1T]
   unsigned int* left_count; // [1]
-  double* partial;          // [2][nblk][2]
-  double* out;              // [8] result block: 0..3 sums, [4] pairs (u64), [5] flags (int), [6] rows reduced (u64)
+  unsigned long long* acc;  // [4] fixed-point sum (lo, hi), zero counts of n_x and n_y
+  double* out;              // [16] result block: 0 sum (double, informative), 1 zeros_x, 2 zeros_y, [4] pairs (u64),
+                            //      [5] flags (int), [6] rows reduced (u64), [8] sum lo (u64), [9] sum hi (i64)
   // optional per-row outputs (device, row order), or NULL
   double* eps_row;
   long long* nx_row;
@@ -92,21 +115,21 @@ struct Prob {
 size_t prob_bytes(const Plan& p, int k1t);
 Prob carve_prob(char* base, const Plan& p, int k1t, int cx, int cy);
 
-// shard of the slot blocks a call works on: blocks whose index maps into rows [row_lo, row_hi) of n
+// shard of the x-buckets a call works on: buckets whose first slot lies in [row_lo, row_hi)
 struct Shard {
-  int64_t row_lo, row_hi, n;
+  int64_t row_lo, row_hi;
 };
 
-cudaError_t init();       // opt-in shared memory sizes (once per process)
+cudaError_t init();       // opt-in shared memory sizes (once per device)
 
-// cols / probs: DEVICE arrays.  Launch counts are returned through *launches.
-cudaError_t colsort(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches);
+// cols / probs: DEVICE arrays.  Launch counts are added to *launches.
+cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches);
 cudaError_t layout(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches);
 cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, int k, const Shard& sh, int sm_count,
                 cudaStream_t s, int* launches);
 cudaError_t count_psi(const Col* cols, const Prob* probs, int nprob, const Plan& p, const Shard& sh, const double* psi_tab,
                       int tab_n, cudaStream_t s, int* launches);
-// folds the block partials of every problem in a fixed order into probs[p].out[0..3] and ORs the column flags into out[5]
+// fills probs[p].out from the accumulators and ORs the column flags into out[5]
 cudaError_t finalize(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches);
 
 }  // namespace k2

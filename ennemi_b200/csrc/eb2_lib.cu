@@ -103,6 +103,7 @@ struct Ctx {
   size_t pinned_cap = 0;
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
+  int last_pipeline = 0;              // 1: the last KSG call on this lane went through the bivariate pipeline
   DevShared* shared = nullptr;
   // per-call workspace: one block per lane, bump-allocated by Scratch and kept across calls (calls on a lane are
   // serialised and stream-ordered, so the next call may reuse it); grown after a call that did not fit
@@ -116,7 +117,7 @@ struct Ctx {
   // same device addresses, so its ~45 launches can be replayed as one graph launch.  Entries die with the workspace
   // or the tile tables they reference.
   struct GraphEntry {
-    int64_t key[8];
+    int64_t key[10];
     cudaGraphExec_t exec = nullptr;
     void* host_result = nullptr;      // pinned block the graph's last node copies the result into
     int64_t rows = 0;
@@ -994,13 +995,17 @@ void export_outputs(Scratch& s, const PointSet& ps, const double* eps, const int
 // gathers sums + work counter + non-finite flag, synchronises, fills the partial block and timings
 thread_local bool g_skip_timing = false;   // set by batched calls for all but their last task
 
-struct Res { double v[4]; unsigned long long pairs; int nonfinite; int pad; unsigned long long rows; };
-static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40 && offsetof(Res, rows) == 48 && sizeof(Res) == 56,
+struct Res { double v[4]; unsigned long long pairs; int nonfinite; int pad; unsigned long long rows; double spare;
+             unsigned long long fix_lo; long long fix_hi; };
+static_assert(offsetof(Res, pairs) == 32 && offsetof(Res, nonfinite) == 40 && offsetof(Res, rows) == 48 &&
+              offsetof(Res, fix_lo) == 64 && offsetof(Res, fix_hi) == 72 && sizeof(Res) == 80,
               "Res mirrors the device result block");
+constexpr int kResDoubles = 16;
 
 // the synchronised result block -> error code / partial block
 int parse_result(const Res* h, int64_t rows, double* partial) {
-  if (rows < 0) rows = static_cast<int64_t>(h->rows);      // the bivariate pipeline counts the rows it reduced on the device
+  const bool fixed = rows < 0;
+  if (fixed) rows = static_cast<int64_t>(h->rows);      // the bivariate pipeline counts the rows it reduced on the device
   if (h->nonfinite & k2::kFlagOverflow) return EB2_ERR_RETRY_GENERAL;     // internal: the caller repeats on the general path
   if (h->nonfinite & 8) {
     g_data_flags = h->nonfinite;
@@ -1019,6 +1024,15 @@ int parse_result(const Res* h, int64_t rows, double* partial) {
     partial[EB2_P_ZERO_C] = h->v[3];
     partial[EB2_P_ROWS] = static_cast<double>(rows);
     partial[EB2_P_PAIRS] = static_cast<double>(h->pairs);
+    if (fixed) {
+      // the bivariate pipeline's exact sum: 128-bit two's complement in units of 2^-48, as four 32-bit limbs that
+      // doubles carry (and add, over ranks) without rounding
+      partial[EB2_P_FIX0] = static_cast<double>(h->fix_lo & 0xffffffffull);
+      partial[EB2_P_FIX0 + 1] = static_cast<double>(h->fix_lo >> 32);
+      partial[EB2_P_FIX0 + 2] = static_cast<double>(static_cast<unsigned long long>(h->fix_hi) & 0xffffffffull);
+      partial[EB2_P_FIX0 + 3] = static_cast<double>(h->fix_hi >> 32);
+      partial[EB2_P_FIXED] = 1.0;
+    }
   }
   return EB2_OK;
 }
@@ -1102,7 +1116,7 @@ bool graph_enabled() {
 }
 
 // entry of this call signature in the lane's graph cache (created on first sight; most recently used last)
-Ctx::GraphEntry* graph_entry(Ctx& c, const int64_t (&key)[8]) {
+Ctx::GraphEntry* graph_entry(Ctx& c, const int64_t (&key)[10]) {
   for (size_t i = 0; i < c.graphs.size(); ++i) {
     if (std::memcmp(c.graphs[i].key, key, sizeof key) == 0) {
       if (i + 1 != c.graphs.size()) {
@@ -1132,8 +1146,8 @@ CallInit begin_call(Scratch& s) {
   CU(cudaSetDevice(c.dev));
   if (!g_skip_timing) record_event(s, c.ev[0]);
   CallInit ci;
-  s.result = s.dev<double>(8);
-  CU(cudaMemsetAsync(s.result, 0, sizeof(double) * 8, c.stream));
+  s.result = s.dev<double>(kResDoubles);
+  CU(cudaMemsetAsync(s.result, 0, sizeof(double) * kResDoubles, c.stream));
   ci.pairs = reinterpret_cast<unsigned long long*>(s.result + 4);
   ci.nonfinite = reinterpret_cast<int*>(s.result + 5);
   return ci;
@@ -1152,10 +1166,18 @@ double psi_host(double y) {
 
 // mean over rows of (psi(a) + psi(b) - psi(c)) given the finite sum and the zero counters:
 // a zero count anywhere in an array turns that array's psi into a scalar +inf in the reference
+// the digamma sum of a partial block: the bivariate pipeline's exact fixed-point total when present
+double partial_sum(const double* partial) {
+  if (!(partial[EB2_P_FIXED] > 0)) return partial[EB2_P_SUM];
+  __int128 total = 0;
+  for (int i = 3; i >= 0; --i) total = (total << 32) + static_cast<__int128>(std::llround(partial[EB2_P_FIX0 + i]));
+  return std::ldexp(static_cast<double>(total), -48);
+}
+
 double psi_mean(const double* partial, int64_t n) {
   const double inf = std::numeric_limits<double>::infinity();
   const bool za = partial[EB2_P_ZERO_A] > 0, zb = partial[EB2_P_ZERO_B] > 0, zc = partial[EB2_P_ZERO_C] > 0;
-  if (!(za || zb || zc)) return partial[EB2_P_SUM] / static_cast<double>(n);
+  if (!(za || zb || zc)) return partial_sum(partial) / static_cast<double>(n);
   return (za ? inf : 0.0) + (zb ? inf : 0.0) - (zc ? inf : 0.0);   // inf - inf = nan, as numpy gives
 }
 
@@ -1276,6 +1298,12 @@ int eb2_last_timing(int dev, double* ms, int* launches) {
   if (ms) for (int i = 0; i < 5; ++i) ms[i] = c.last_ms[i];
   if (launches) *launches = c.last_launches;
   return EB2_OK;
+}
+
+int eb2_last_pipeline(int dev) {
+  const int ord = dev & 0xff, lane = (dev >> 8) & 0xff;
+  if (dev < 0 || ord >= kMaxDev || lane >= kMaxLanes || !g_ctx[ord * kMaxLanes + lane].ready) return -1;
+  return g_ctx[ord * kMaxLanes + lane].last_pipeline;
 }
 
 // ---- device column cache ---------------------------------------------------------------------------
@@ -1485,9 +1513,8 @@ double* run_k2(Scratch& s, const k2::Plan& plan, const double* raw, int64_t n, i
   k2::Prob* dprob = s.dev<k2::Prob>(1);
   k2_setup_kernel<<<1, 1, 0, st>>>(hc0, hc1, hp, dcols, dprob);
   s.launches++;
-  CU(cudaMemsetAsync(hp.partial, 0, sizeof(double) * 4 * plan.nblk, st));     // blocks of other shards read as zero
-  const k2::Shard sh{row_lo, row_hi, n};
-  CU(k2::colsort(dcols, 2, plan, st, &s.launches));
+  const k2::Shard sh{row_lo, row_hi};
+  CU(k2::colgrid(dcols, 2, plan, st, &s.launches));
   CU(k2::layout(dcols, dprob, 1, plan, st, &s.launches));
   mark(s, 1);
   CU(k2::knn(dcols, dprob, 1, plan, k, sh, c.sm_count, st, &s.launches));
@@ -1521,9 +1548,10 @@ static int ksg_rows_once(int dev, const Input& in, int64_t n, int k, int64_t row
                            !(flags & EB2_FLAG_BRUTE_COUNT) &&
                            (use_k2 || (n >= partition_min_rows() && !getenv("EB2_NO_CELLS") && !getenv("EB2_CELL_SORT"))) &&
                            !eps_out && !nx_out && !ny_out && partial && !g_skip_timing;
-    const int64_t gkey[8] = {static_cast<int64_t>(reinterpret_cast<intptr_t>(in.coords)), n, k,
-                             static_cast<int64_t>(flags) | (use_k2 ? int64_t(1) << 40 : 0), row_lo, row_hi,
-                             static_cast<int64_t>(reinterpret_cast<intptr_t>(c.arena)), static_cast<int64_t>(c.arena_cap)};
+    const int64_t gkey[10] = {static_cast<int64_t>(reinterpret_cast<intptr_t>(in.coords)), n, k,
+                              static_cast<int64_t>(flags) | (use_k2 ? int64_t(1) << 40 : 0), row_lo, row_hi,
+                              static_cast<int64_t>(reinterpret_cast<intptr_t>(c.arena)), static_cast<int64_t>(c.arena_cap),
+                              0, 0};
     if (graphable) {
       Ctx::GraphEntry* ge = graph_entry(c, gkey);
       if (ge->exec) return graph_replay(c, *ge, partial);
@@ -1537,6 +1565,7 @@ static int ksg_rows_once(int dev, const Input& in, int64_t n, int k, int64_t row
     }
     CallInit ci = begin_call(s);
     const double* raw = nullptr;
+    c.last_pipeline = use_k2 ? 1 : 0;
     if (use_k2) {
       raw = stage_input(s, in, 2, n, ci.nonfinite, false);        // (the bucket count kernel checks for non-finite values)
       double* out4 = run_k2(s, plan, raw, n, k, row_lo, row_hi, eps_out, nx_out, ny_out);
@@ -1777,7 +1806,7 @@ int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pa
     }
     k2::Col* dcols = s.dev<k2::Col>(nvar);
     CU(cudaMemcpyAsync(dcols, hcols, sizeof(k2::Col) * nvar, cudaMemcpyHostToDevice, st));
-    CU(k2::colsort(dcols, nvar, plan, st, &s.launches));
+    CU(k2::colgrid(dcols, nvar, plan, st, &s.launches));
     record_event(s, c.ev[1]);
     // 2. the pairs, in batches sized to a workspace budget
     const size_t pbytes = k2::prob_bytes(plan, k1t);
@@ -1785,16 +1814,16 @@ int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pa
     if (const char* e = getenv("EB2_PAIR_BATCH_MB")) budget = size_t(atoll(e)) << 20;     // tuning knob
     const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(npairs, static_cast<int64_t>(budget / pbytes)));
     char* pscratch = s.dev<char>(pbytes * batch);
-    double* outs = s.dev<double>(static_cast<size_t>(npairs) * 8);
-    CU(cudaMemsetAsync(outs, 0, sizeof(double) * 8 * npairs, st));
+    double* outs = s.dev<double>(static_cast<size_t>(npairs) * kResDoubles);
+    CU(cudaMemsetAsync(outs, 0, sizeof(double) * kResDoubles * npairs, st));
     k2::Prob* dprobs = s.dev<k2::Prob>(batch);
-    const k2::Shard whole{0, n, n};
+    const k2::Shard whole{0, n};
     for (int64_t p0 = 0; p0 < npairs; p0 += batch) {
       const int m = static_cast<int>(std::min<int64_t>(batch, npairs - p0));
       k2::Prob* hp = s.host<k2::Prob>(m);
       for (int t = 0; t < m; ++t) {
         hp[t] = k2::carve_prob(pscratch + pbytes * t, plan, k1t, pairs[2 * (p0 + t)], pairs[2 * (p0 + t) + 1]);
-        hp[t].out = outs + 8 * (p0 + t);
+        hp[t].out = outs + kResDoubles * (p0 + t);
       }
       CU(cudaMemcpyAsync(dprobs, hp, sizeof(k2::Prob) * m, cudaMemcpyHostToDevice, st));
       CU(k2::layout(dcols, dprobs, m, plan, st, &s.launches));
@@ -1805,14 +1834,14 @@ int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pa
     record_event(s, c.ev[2]);
     record_event(s, c.ev[3]);
     record_event(s, c.ev[4]);
-    static_assert(sizeof(Res) <= 8 * sizeof(double), "result block");
-    std::vector<double> hout(static_cast<size_t>(npairs) * 8);
-    CU(cudaMemcpyAsync(hout.data(), outs, sizeof(double) * 8 * npairs, cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(Res) <= kResDoubles * sizeof(double), "result block");
+    std::vector<double> hout(static_cast<size_t>(npairs) * kResDoubles);
+    CU(cudaMemcpyAsync(hout.data(), outs, sizeof(double) * kResDoubles * npairs, cudaMemcpyDeviceToHost, st));
     record_event(s, c.ev[5]);
     CU(cudaStreamSynchronize(st));
     read_phase_times(c);
     c.last_launches = s.launches;
-    for (int64_t t = 0; t < npairs; ++t) std::memcpy(&res[t], hout.data() + 8 * t, sizeof(Res));
+    for (int64_t t = 0; t < npairs; ++t) std::memcpy(&res[t], hout.data() + kResDoubles * t, sizeof(Res));
     return EB2_OK;
   });
   if (rc) return rc;
@@ -1825,8 +1854,8 @@ int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pa
       status[t] = EB2_ERR_NONFINITE | ((h.nonfinite & 0xff) << 8);
     } else {
       status[t] = 0;
-      double partial[EB2_P_LEN] = {0};
-      partial[EB2_P_SUM] = h.v[0]; partial[EB2_P_ZERO_A] = h.v[1]; partial[EB2_P_ZERO_B] = h.v[2]; partial[EB2_P_ZERO_C] = h.v[3];
+      double partial[EB2_P_LEN];
+      parse_result(&h, -1, partial);
       eb2_ksg_mi_finish(partial, n, k, values + t);
     }
   }

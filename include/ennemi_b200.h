@@ -15,7 +15,7 @@
  *    device `dev` (used to measure the kernels with inputs already resident in HBM).
  *  - optional outputs (eps_out, count outputs) may be NULL; when given they are host arrays of
  *    length n in the caller's original row order.
- *  - `partial` is an 8-double block of raw sums for the rows [row_lo, row_hi) (see EB2_P_*),
+ *  - `partial` is an EB2_P_LEN-double block of raw sums for the rows [row_lo, row_hi) (see EB2_P_*),
  *    so that query rows can be sharded over GPUs/ranks and combined with one sum-allreduce;
  *    eb2_*_finish turns the (summed) block into the estimate.
  *  - return value: 0 on success, an EB2_ERR_* code otherwise; eb2_last_error() gives the
@@ -72,7 +72,11 @@ extern "C" {
 #define EB2_P_ZERO_C 3 /* ... third count */
 #define EB2_P_ROWS 4  /* rows reduced */
 #define EB2_P_PAIRS 5 /* point pairs evaluated by the all-pairs kernels (work counter for the roofline) */
-#define EB2_P_LEN 8
+#define EB2_P_FIX0 8  /* [8..11]: the bivariate pipeline's digamma sum as an exact 128-bit fixed-point integer (units of
+                         2^-48), four 32-bit limbs, least significant first, the last one signed: integer-valued doubles
+                         add exactly, so a sum of partial blocks over shards / ranks is independent of their number */
+#define EB2_P_FIXED 12 /* > 0 when the limbs are present (then they, not EB2_P_SUM, define the sum) */
+#define EB2_P_LEN 16
 
 EB2_API int eb2_init(void);            /* optional; creates the per-device contexts eagerly */
 EB2_API int eb2_shutdown(void);        /* frees every device workspace */
@@ -140,6 +144,9 @@ EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, in
  * ms[0] total device span (first H2D to last D2H), ms[1] k-NN kernel, ms[2] marginal counting,
  * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
 EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
+/* 1 when the last eb2_ksg_mi* call on `dev` ran on the bivariate pipeline (sort-free grid), 0 when the general path
+ * took it (size / k / flags outside the pipeline, or a bucket overflow on heavily tied data), -1 without a context */
+EB2_API int eb2_last_pipeline(int dev);
 
 /* ---- device-resident columns (lag sweeps and pairwise_mi upload every
  * variable once instead of once per task; the reference's per-task _rescale_data,

@@ -58,7 +58,7 @@ def test_argument_errors_do_not_need_a_device():
     assert b"NULL" in lib.eb2_last_error()
     z = np.zeros((40, 8))        # 40 dimensions > EB2_MAX_DIM (32)
     assert lib.eb2_entropy(0, z.ctypes.data, 8, 40, 3, 0, ctypes.byref(val), None) == _native.ERR_UNSUPPORTED
-    part = np.zeros(8)
+    part = np.zeros(_native.P_LEN)
     part[_native.P_SUM] = 10.0
     v = _native.ksg_mi_finish(part, 5, 1)     # psi(5) + psi(1) - 10/5, host-only arithmetic
     import oracle
@@ -67,3 +67,20 @@ def test_argument_errors_do_not_need_a_device():
     assert _native.ksg_mi_finish(part, 5, 1) == -np.inf
     part[_native.P_ZERO_C] = 1
     assert np.isnan(_native.cmi_finish(part, 5, 1))
+    # the bivariate pipeline's exact sum: 128-bit fixed point (2^-48 units) in four 32-bit limbs, the last one signed;
+    # limbs of several shards add as doubles without rounding, whatever the number of shards
+    def limbs(total):
+        t = total & ((1 << 128) - 1)
+        out = [(t >> (32 * i)) & 0xffffffff for i in range(4)]
+        out[3] -= (1 << 32) if out[3] >= (1 << 31) else 0
+        return out
+    want = -1234.567890123
+    pieces = [int(round(x * 2 ** 48)) for x in (want * 0.25, want * 0.5, want * 0.125, want * 0.125)]
+    fixed = np.zeros(_native.P_LEN)
+    for q in pieces:
+        fixed[8:12] += limbs(q)
+        fixed[12] += 1
+    fixed[_native.P_SUM] = 777.0              # ignored when the limbs are present
+    v = _native.ksg_mi_finish(fixed, 5, 1)
+    exact = sum(pieces) / 2 ** 48
+    assert abs(v - (oracle.psi(np.array([5]))[0] + oracle.psi(np.array([1]))[0] - exact / 5)) < 1e-12

@@ -240,7 +240,9 @@ def test_graph_replay_matches_eager(monkeypatch):
     ptr = int(dev.data_ptr())
 
     def call(lo=0, hi=n):
-        return nat.ksg_mi_rows(ptr, n, 3, lo, hi, flags=nat.FLAG_DEVICE_INPUT)
+        part = nat.ksg_mi_rows(ptr, n, 3, lo, hi, flags=nat.FLAG_DEVICE_INPUT)
+        part[nat.P_PAIRS] = 0.0          # the work counter depends on the (unordered) slot layout of the run, the result does not
+        return part
 
     monkeypatch.setenv("EB2_GRAPH", "0")
     eager = call()
