@@ -427,11 +427,22 @@ def run_gpu(args):
         ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
         ebd.enable_row_sharding(True)
         ms_s, _, knn_s, _ = timed_steps(step_sharded, args.steps, args.warmup)
+        # what the exchange alone costs: the same all-reduce of a partial block, nothing else
+        blk = np.zeros(nat.P_LEN)
+        for _ in range(5):
+            ebd._all_reduce_sum(blk)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ebd._all_reduce_sum(blk)
+        reduce_ms = (time.perf_counter() - t0) / 20 * 1e3
         sharded = {"value": 1e3 / (ms_s / args.steps), "unit": UNIT, "scaling": "strong", "ms_per_step": ms_s / args.steps,
-                   "knn_ms": knn_s / args.steps, "mi": last["value"],
-                   "note": "configs[1]: ONE N=1e6 estimate, query rows sharded over the GPUs (full point set on every GPU), "
-                           "one NCCL all-reduce of the 8-double partial block; latency of a single estimate, bounded below by "
-                           "the per-rank sort/layout"}
+                   "knn_ms": knn_s / args.steps, "mi": last["value"], "phase_ms": dict(last["phases"]),
+                   "all_reduce_ms": reduce_ms, "speedup_vs_one_gpu_step": None,
+                   "note": "configs[1]: ONE N=1e6 estimate, the x-buckets (and with them the query rows) sharded over the GPUs; every "
+                           "rank builds the whole grid (the point set is replicated), searches and counts its own buckets, and one "
+                           "NCCL all-reduce sums the partial blocks, whose digamma sum is an exact integer: the value is bit-identical "
+                           "for every number of GPUs.  Latency of a single estimate; the replicated grid build bounds it below"}
     units = world          # estimates per step
 
     # second half of BASELINE.json's metric: pairwise_mi wall time, 64 variables x N = 100,000 (configs[3]),

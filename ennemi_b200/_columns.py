@@ -126,6 +126,8 @@ class ColumnStore:
         # whole-column mean/std of every block column computed right after the upload, in one call
         # (the windows of every pairwise_mi task; lagged windows are computed on demand)
         self.full_stats = full_stats
+        # set by the API when every rank of a fan-out job is known to reach the upload (a collective)
+        self.sharded_upload = False
 
     def add(self, column: np.ndarray) -> int:
         key = _new_key()
@@ -178,7 +180,8 @@ class ColumnStore:
                 done = [key]
             else:
                 block, keys = self._blocks[bid]
-                _native.cache_put_block(keys, block, dev=dev)
+                if not self._put_block_sharded(keys, block, dev):
+                    _native.cache_put_block(keys, block, dev=dev)
                 done = keys
                 n = block.shape[0]
                 if self.full_stats and n >= DEVICE_STATS_MIN_ROWS:
@@ -192,6 +195,33 @@ class ColumnStore:
             with self._lock:
                 self._inflight.pop(unit, None)
             mine.set()
+
+    def _put_block_sharded(self, keys, block: np.ndarray, dev: int) -> bool:
+        """One process per GPU with task fan-out on (every rank makes the same call with the same data): each rank
+        uploads only its 1/G of the block's rows and the slices are all-gathered over NVLink, so the host-to-device
+        copy - the largest fixed cost of a multi-GPU ``pairwise_mi`` - is shared out.  False: not applicable."""
+        if not self.sharded_upload or block.shape[0] < 8 * 1024:
+            return False
+        from . import distributed
+        if not distributed.task_fanout_enabled() or distributed._dist().get_backend() != "nccl":
+            return False
+        import torch
+        rank, size = distributed.world()
+        n, ncols = block.shape
+        ld = _native.block_layout(block)
+        if ld != ncols:
+            return False
+        per = -(-n // size)
+        tdev = torch.device("cuda", _devices.ordinal(dev))
+        mine = torch.zeros((per, ncols), dtype=torch.float64, device=tdev)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        if hi > lo:
+            mine[: hi - lo].copy_(torch.from_numpy(block[lo:hi]), non_blocking=False)
+        full = torch.empty((per * size, ncols), dtype=torch.float64, device=tdev)
+        distributed._dist().all_gather_into_tensor(full, mine)
+        torch.cuda.current_stream(tdev).synchronize()
+        _native.cache_put_block_dev(keys, int(full.data_ptr()), n, ncols, dev=dev)
+        return True
 
     def cached_desc(self, tag: tuple):
         return self._descs.get(tag)
@@ -252,7 +282,7 @@ class ColsTask:
     """A continuous (x, y[, cond]) task on cached columns; ``run()`` returns the estimate."""
 
     __slots__ = ("store", "xkey", "ykey", "zkeys", "xview", "yview", "cond", "lag", "hi", "lo", "cond_lag", "k",
-                 "preprocess", "n_total", "single_use")
+                 "preprocess", "n_total", "single_use", "share_prepared")
 
     def __init__(self, store, xkey, ykey, zkeys, xview, yview, cond, lag, hi, lo, cond_lag, k, preprocess):
         self.store, self.xkey, self.ykey, self.zkeys = store, xkey, ykey, zkeys
@@ -260,6 +290,10 @@ class ColsTask:
         self.lag, self.hi, self.lo, self.cond_lag, self.k, self.preprocess = lag, hi, lo, cond_lag, k, preprocess
         self.n_total = len(yview)
         self.single_use = False      # set by the API when the call consists of this one task
+        # prepared (rescaled + sorted) variables are kept on the device for the other tasks of the call only where
+        # descriptors recur (pairwise_mi: every column 63 times); a lag sweep's x windows are used once each, and
+        # caching them would grow device memory with nlags * nvar (set by the API)
+        self.share_prepared = False
 
     def describe(self, dev: int, in_call_stats: bool = False):
         """(descriptors, n) of this task for device ``dev``: uploads what is missing, computes (cached)
@@ -375,7 +409,7 @@ class ColsTask:
                 return self._estimate(dev, descs, n, _native.FLAG_SINGLE_USE | _native.FLAG_DEVICE_STATS)
             except _native.ConstantWindow:       # rare: the reference's constant-data warning path needs the value of std
                 descs, n = self.describe(dev, False)
-        return self._estimate(dev, descs, n, _native.FLAG_SINGLE_USE if self.single_use else 0)
+        return self._estimate(dev, descs, n, 0 if self.share_prepared and not self.single_use else _native.FLAG_SINGLE_USE)
 
     def _estimate(self, dev: int, descs, n: int, flags: int) -> float:
         try:
@@ -473,6 +507,7 @@ def run_batch(tasks: List["ColsTask"]) -> List[float]:
     dev = _devices.current()
     described = [t.describe(dev) for t in tasks]
     n = described[0][1]
-    values, status = _native.mi_cols_batch([d for d, _ in described], n, tasks[0].k, dev=dev)
+    values, status = _native.mi_cols_batch([d for d, _ in described], n, tasks[0].k, dev=dev,
+                                           flags=0 if tasks[0].share_prepared else _native.FLAG_SINGLE_USE)
     _check_status(status)
     return [float(v) for v in values]

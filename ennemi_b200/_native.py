@@ -35,7 +35,7 @@ EXPORTS = (
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
-    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs", "eb2_last_pipeline",
+    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs", "eb2_last_pipeline", "eb2_cache_put_block_dev",
 )
 
 _lib = None
@@ -92,6 +92,7 @@ def load():
         lib.eb2_cache_put.argtypes = [_int, ctypes.c_uint64, _vp, _i64]
         lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
         lib.eb2_cache_put_block.argtypes = [_int, _vp, _int, _vp, _i64, _i64]
+        lib.eb2_cache_put_block_dev.argtypes = [_int, _vp, _int, _vp, _i64, _i64]
         lib.eb2_cache_stats_many.argtypes = [_int, _vp, _vp, _int, _i64, _i64, _vp, _vp]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
@@ -372,6 +373,14 @@ def cache_put_block(keys: Sequence[int], block: np.ndarray, dev: int = 0) -> Non
         raise ValueError("cache_put_block: need a 2-D float64 array with unit column stride and one key per column")
     karr = np.asarray(keys, dtype=np.uint64)
     rc = lib.eb2_cache_put_block(dev, karr.ctypes.data, len(keys), block.ctypes.data, block.shape[0], ld)
+    if rc:
+        _raise(rc)
+
+
+def cache_put_block_dev(keys: Sequence[int], ptr: int, n: int, ld: int, dev: int = 0) -> None:
+    """:func:`cache_put_block` from a row-major block that already is in device memory at ``ptr`` on ``dev``."""
+    karr = np.asarray(keys, dtype=np.uint64)
+    rc = load().eb2_cache_put_block_dev(dev, karr.ctypes.data, len(keys), ptr, n, ld)
     if rc:
         _raise(rc)
 

@@ -181,7 +181,12 @@ def estimate_mi(y, x, lag=0, *, k: int = 3, cond=None, cond_lag=0, mask=None,
     ``preprocess`` rescales continuous variables to unit variance and adds fixed-seed 1e-10 noise;
     ``drop_nan`` removes rows with NaNs; ``normalize`` returns correlation coefficients
     (:func:`normalize_mi`).  ``max_threads`` bounds the number of concurrent tasks (GPU workers);
-    ``callback(var_index, lag)`` is invoked after each finished task.  (``_driver.py:229-361``)
+    ``callback(var_index, lag)`` is invoked once per task after it has finished.  (``_driver.py:229-361``)
+
+    Callback timing differs from the reference's thread pool: tasks on device-resident columns are estimated in
+    batches (all unconditional tasks of a GPU in ONE library call), so their callbacks arrive in bursts when a batch
+    returns; with task fan-out over ranks (:mod:`ennemi_b200.distributed`) every rank sees the callbacks of its own
+    share of the tasks only.
     """
     x_arr = np.asarray(x)
     y_arr = np.asarray(y)
@@ -264,8 +269,9 @@ def pairwise_mi(data, *, k: int = 3, cond=None, mask=None, discrete=False, prepr
 
     ``discrete`` marks discrete columns (scalar or one flag per column); ``cond`` is allowed only
     when the data are all continuous or all discrete.  Other options as in :func:`estimate_mi`.
-    ``callback(i, j)`` fires after each pair.  A ``DataFrame`` in gives a ``DataFrame`` out.
-    (``_driver.py:540-624, 680-723``)
+    ``callback(i, j)`` fires once per pair after it has finished (in bursts: the pairs of a GPU are estimated
+    by one library call; with task fan-out over ranks each rank sees its own share only - see
+    :func:`estimate_mi`).  A ``DataFrame`` in gives a ``DataFrame`` out.  (``_driver.py:540-624, 680-723``)
     """
     data_arr = np.asarray(data)
     cond_arr = None if cond is None else np.column_stack((np.asarray(cond),))
@@ -286,10 +292,13 @@ def pairwise_mi(data, *, k: int = 3, cond=None, mask=None, discrete=False, prepr
     store = _device_store([data_arr, cond_arr], mask_arr, drop_nan, bool(flags.any()))
     if store is not None:
         store.full_stats = bool(preprocess)
+        store.sharded_upload = len(pairs) >= 64        # (every rank has tasks, so every rank reaches the upload)
         keys = store.add_columns(data_arr)
         zkeys = [] if cond_arr is None else store.add_columns(cond_arr)
         tasks = [ColsTask(store, keys[i], keys[j], zkeys, data_arr[:, i], data_arr[:, j], cond_arr, 0, 0, 0,
                           np.atleast_1d(zero_lag), k, preprocess) for i, j in pairs]
+        for t in tasks:
+            t.share_prepared = True
     else:
         tasks = [MiTask(data_arr[:, i], data_arr[:, j], 0, 0, 0, k, mask_arr, cond_arr, zero_lag,
                         flags[i], flags[j], preprocess, drop_nan) for i, j in pairs]

@@ -395,14 +395,14 @@ __global__ void np_tree_kernel(const NpCols a, const int2* children, const NpLev
 
 // (n x ncols) row-major block -> ncols separate columns (eb2_cache_put_block): 32 x 32 tiles through shared
 // memory so that both the reads (along a row of the block) and the writes (along a column) are coalesced
-__global__ void deinterleave_kernel(const double* __restrict__ block, long long n, int ncols, double* const* __restrict__ cols) {
+__global__ void deinterleave_kernel(const double* __restrict__ block, long long n, int ncols, long long ld, double* const* __restrict__ cols) {
   __shared__ double tile[32][33];
   const long long r0 = static_cast<long long>(blockIdx.x) * 32;
   const int c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const long long r = r0 + i;
     const int cc = c0 + threadIdx.x;
-    if (r < n && cc < ncols) tile[i][threadIdx.x] = block[r * ncols + cc];
+    if (r < n && cc < ncols) tile[i][threadIdx.x] = block[r * ld + cc];
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += 8) {

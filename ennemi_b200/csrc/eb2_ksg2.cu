@@ -51,7 +51,7 @@ __device__ __forceinline__ int bucket_fn(const BucketFn& f, double v) {
     const int mid = (lo + hi) >> 1;
     if (f.split[mid] < v) lo = mid + 1; else hi = mid;
   }
-  return lo * kSub + lin_cell(v, f.clo[lo], f.csc[lo], kSub);
+  return lo;                                   // (kSub == 1: the buckets are the quantile stretches themselves)
 }
 
 // in-place exclusive prefix sum of a[0 .. m) in shared memory, m <= 16 * blockDim.x, by the whole CTA;
@@ -153,23 +153,22 @@ __global__ void __launch_bounds__(kSplitThreads) split_tables_kernel(const Col* 
     c.clo[q] = lo;
     c.csc[q] = (hi > lo && hi - lo < d_inf()) ? (double)kSub / (hi - lo) : 0.0;
     if (q < Bc - 1) c.split[q] = hi;
+    // bounds of the bucket's values for the search kernels: the values of bucket q lie in (vlo, vhi]
+    c.vlo[q] = q == 0 ? -d_inf() : lo;
+    c.vhi[q] = q == Bc - 1 ? d_inf() : hi;
   }
   for (int b = threadIdx.x; b <= NB; b += blockDim.x) { c.count[b] = 0; c.fill[b] = 0; }
 }
 
 // ---- colgrid 2: bucket of every row, rows per bucket ---------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsB) bucket_hist_kernel(const Col* cols, long long n, int Bc, int NB) {
-  __shared__ double s_split[kMaxCoarse], s_clo[kMaxCoarse], s_csc[kMaxCoarse];
+  __shared__ double s_split[kMaxCoarse];
   __shared__ int s_hist[kMaxBuckets];
   const Col c = cols[blockIdx.y];
-  for (int q = threadIdx.x; q < Bc; q += blockDim.x) {
-    s_split[q] = q < Bc - 1 ? c.split[q] : d_inf();
-    s_clo[q] = c.clo[q];
-    s_csc[q] = c.csc[q];
-  }
+  for (int q = threadIdx.x; q < Bc; q += blockDim.x) s_split[q] = q < Bc - 1 ? c.split[q] : d_inf();
   for (int b = threadIdx.x; b < NB; b += blockDim.x) s_hist[b] = 0;
   __syncthreads();
-  const BucketFn fn{s_split, s_clo, s_csc, Bc};
+  const BucketFn fn{s_split, nullptr, nullptr, Bc};
   const long long r0 = (long long)blockIdx.x * kHistRows;
   bool bad = false;
 #pragma unroll 4
@@ -229,9 +228,8 @@ __global__ void __launch_bounds__(kThreadsB) bucket_scatter_kernel(const Col* co
 
 // ---- colgrid 4: the values of every bucket grouped into fine cells (about one per cell) ----------------------------
 // The cell map of bucket b is linear over the stretch the bucket function assigns to it (split[b-1], split[b]] (the
-// outermost sample values at the two ends; values beyond them clamp into the end cells).  vlo / vhi are bounds of the
-// bucket's values for the search kernels: values of bucket b lie in (vlo, vhi].
-static_assert(kSub == 1, "fine_cells_kernel takes the bucket bounds from the quantile stretches");
+// outermost sample values at the two ends; values beyond them clamp into the end cells).
+static_assert(kSub == 1, "fine_cells_kernel takes the bucket bounds from the quantile stretches; bucket_fn returns the stretch");
 __global__ void __launch_bounds__(kThreadsB) fine_cells_kernel(const Col* cols, long long n, int NB) {
   __shared__ int s_hist[kMaxCells];
   __shared__ int red[32];
@@ -248,8 +246,6 @@ __global__ void __launch_bounds__(kThreadsB) fine_cells_kernel(const Col* cols, 
   const int G = min(max(len, 1), kMaxCells);
   const double sc = c.csc[b] * (double)G;                   // csc = 1 / width of the stretch (0: degenerate)
   if (threadIdx.x == 0) {
-    c.vlo[b] = b == 0 ? -d_inf() : lo;
-    c.vhi[b] = b == NB - 1 ? d_inf() : c.split[b];
     c.fsc[b] = sc;
     c.ncell[b] = len ? G : 0;
     c.fg[b] = FineGrid{lo, sc, off, len ? G : 0};
@@ -445,51 +441,36 @@ __device__ __forceinline__ void bucket_window(const Prob& pr, int off, int len, 
   }
 }
 
-// Slots [a, e) against one query, in groups of four (eight independent loads in flight, one branch per group).  When a
-// slot of the group passes the exact test, the group's distances are inserted smallest first until the next one no longer
-// beats the k-th distance of the moment - almost always one insertion, so the lanes of a warp (which hit at different
-// slots) spend little time waiting for each other.
-// Slots [skip_a, skip_e) (the seeds) are jumped over.
-template <int K1T>
+// Slots [a, e) against one query, in groups of four (eight independent loads in flight, one branch per group); a group
+// with a slot that passes the exact test is gone through slot by slot.  SKIP: slots [skip_a, skip_e) (the seeds) are
+// jumped over.
+template <int K1T, bool SKIP>
 __device__ __forceinline__ void scan_range(const double* __restrict__ px, const double* __restrict__ py, int a, int e,
                                            double qx, double qy, double (&best)[K1T], double& thr, unsigned long long& np,
                                            int skip_a = 0, int skip_e = 0) {
   if (e > a) np += (unsigned long long)(e - a);
-  const double kInf = d_inf();
-  if (a >= skip_a && a < skip_e) a = skip_e;
+  if (SKIP && a >= skip_a && a < skip_e) a = skip_e;
 #pragma unroll 1
   for (int s = a; s < e; s += 4) {
-    if (s >= skip_a && s < skip_e) s = skip_e;   // (the group that straddles the start of the seeds masks them below)
+    if (SKIP && s >= skip_a && s < skip_e) s = skip_e;   // (a group that straddles the start of the seeds masks them below)
     double dx[4], dy[4];
     bool any = false;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int t = min(s + u, e - 1);           // the last group repeats its final slot; repeats are masked below
-      const bool seeded = t >= skip_a && t < skip_e;
-      dx[u] = seeded ? kInf : fabs(qx - px[t]);
+      dx[u] = fabs(qx - px[t]);
       dy[u] = fabs(qy - py[t]);
+      if (SKIP && t >= skip_a && t < skip_e) dx[u] = d_inf();
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) any = any || (s + u < e && dx[u] < thr && dy[u] < thr);
     if (any) {
-      double d[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) d[u] = (s + u < e) ? fmax(dx[u], dy[u]) : kInf;
-#pragma unroll 1
-      for (int rep = 0; rep < 4; ++rep) {
-        double m = d[0];
-        int w = 0;
-#pragma unroll
-        for (int u = 1; u < 4; ++u) {
-          const bool lt = d[u] < m;
-          m = lt ? d[u] : m;
-          w = lt ? u : w;
+      for (int u = 0; u < 4; ++u) {
+        if (s + u < e && dx[u] < thr && dy[u] < thr) {
+          topk_insert<K1T>(best, fmax(dx[u], dy[u]));
+          thr = best[K1T - 1];
         }
-        if (!(m < thr)) break;                    // (max(dx, dy) < thr  <=>  both differences below thr: the exact test)
-        topk_insert<K1T>(best, m);
-        thr = best[K1T - 1];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = (u == w) ? kInf : d[u];
       }
     }
   }
@@ -554,7 +535,7 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
   {
     int a = 0, e = 0;
     if (valid) bucket_window(pr, off, len, pr.bymin[b], pr.bysc[b], qy, thr, a, e);
-    scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np, sa, se);
+    scan_range<K1T, true>(px, py, a, e, qx, qy, best, thr, np, sa, se);
   }
   // 3. outwards
   int rstart = NB, lend = 0;
@@ -569,7 +550,7 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
         if (j >= NB || (cx.vlo[j] - qx) >= thr) more = false;
         else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); ++j; }
       }
-      scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np);
+      scan_range<K1T, false>(px, py, a, e, qx, qy, best, thr, np);
     }
     if (more) {
       while (j < NB && cx.count[j] == 0) ++j;
@@ -587,7 +568,7 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
         if (j < 0 || (qx - cx.vhi[j]) >= thr) more = false;
         else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); --j; }
       }
-      scan_range<K1T>(px, py, a, e, qx, qy, best, thr, np);
+      scan_range<K1T, false>(px, py, a, e, qx, qy, best, thr, np);
     }
     if (more) {
       while (j >= 0 && cx.count[j] == 0) --j;
@@ -724,33 +705,54 @@ __device__ __forceinline__ int stretch_near(const BucketFn& f, int c, double t) 
 }
 
 // index of the fine cell a threshold t falls into (monotone non-decreasing in t); an empty bucket has no cells of its
-// own and yields the first cell of the next bucket.  c: a stretch near t (updated to t's own).
-__device__ __forceinline__ int cell_index(const GridView& g, int& c, double t) {
-  c = stretch_near(g.fn, c, t);
-  const int b = c * kSub + lin_cell(t, g.fn.clo[c], g.fn.csc[c], kSub);
-  const FineGrid fg = g.fg[b];
+// own and yields the first cell of the next bucket
+__device__ __forceinline__ int cell_of(const FineGrid& fg, double t) {
   return fg.ncell == 0 ? fg.boff : fg.boff + lin_cell(t, fg.vlo, fg.fsc, fg.ncell);
+}
+// ... for a widened pair of thresholds lo_t <= hi_t a few ulps apart (almost always the same bucket: one table load).
+// c: a stretch near lo_t, updated to lo_t's own.
+__device__ __forceinline__ void cell_index_pair(const GridView& g, int& c, double lo_t, double hi_t, int& i_lo, int& i_hi) {
+  c = stretch_near(g.fn, c, lo_t);
+  const FineGrid f1 = g.fg[c];                 // (kSub == 1: bucket = stretch)
+  i_lo = cell_of(f1, lo_t);
+  if (c < g.fn.Bc - 1 && g.fn.split[c] < hi_t) {
+    const FineGrid f2 = g.fg[stretch_near(g.fn, c + 1, hi_t)];
+    i_hi = cell_of(f2, hi_t);
+  } else {
+    i_hi = cell_of(f1, hi_t);
+  }
 }
 
 // #{j : |fl(v - s_j)| <= r} over the whole column (the point itself included): cells strictly between the boundary
 // cells of the two thresholds are inside whatever their values (the thresholds are widened by more than the rounding
-// of the subtraction), values in boundary cells are tested exactly.  c0: the quantile stretch of v.
-__device__ __forceinline__ int grid_count(const GridView& g, int c0, double v, double r) {
-  if (!(r >= 0.0)) return 0;
+// of the subtraction), values in boundary cells are tested exactly.  In two steps so that the table loads of the two
+// marginals of a query are in flight together: count_plan (cell indices -> slot ranges), count_run (the exact tests).
+struct CountPlan {
+  int a1, e1, a2, e2, whole;
+};
+// c0: the quantile stretch of v
+__device__ __forceinline__ CountPlan count_plan(const GridView& g, int c0, double v, double r) {
+  CountPlan p{0, 0, 0, 0, 0};
+  if (!(r >= 0.0)) return p;
   const double w = (fabs(v) + r) * kSlack;
-  int c = c0;
-  const int i2 = cell_index(g, c, (v - r) + w);
-  const int i1 = cell_index(g, c, (v - r) - w);
+  int c = c0, i1, i2, i3, i4;
+  cell_index_pair(g, c, (v - r) - w, (v - r) + w, i1, i2);
   c = c0;
-  const int i3 = cell_index(g, c, (v + r) - w);
-  const int i4 = cell_index(g, c, (v + r) + w);
-  int cnt = 0;
-  const int a1 = g.fstart[i1], e1 = g.fstart[i2 + 1];
+  cell_index_pair(g, c, (v + r) - w, (v + r) + w, i3, i4);
+  p.a1 = g.fstart[i1];
+  p.e1 = g.fstart[i2 + 1];
   const int i3b = max(i3, i2 + 1);
-  const int a2 = i4 >= i3b ? g.fstart[i3b] : 0, e2 = i4 >= i3b ? g.fstart[i4 + 1] : 0;
-  for (int s = a1; s < e1; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
-  if (i3b > i2 + 1) cnt += a2 - e1;                        // whole cells between the boundaries
-  for (int s = a2; s < e2; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
+  if (i4 >= i3b) {
+    p.a2 = g.fstart[i3b];
+    p.e2 = g.fstart[i4 + 1];
+    if (i3b > i2 + 1) p.whole = p.a2 - p.e1;             // whole cells between the boundaries
+  }
+  return p;
+}
+__device__ __forceinline__ int count_run(const GridView& g, const CountPlan& p, double v, double r) {
+  int cnt = p.whole;
+  for (int s = p.a1; s < p.e1; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
+  for (int s = p.a2; s < p.e2; ++s) cnt += (int)(fabs(v - g.fval[s]) <= r);
   return cnt;
 }
 
@@ -758,19 +760,19 @@ __device__ __forceinline__ double psi_lookup(const double* tab, int tab_n, int c
 
 __global__ void __launch_bounds__(kThreadsB) count_psi_kernel(const Col* cols, const Prob* probs, long long n, int Bc,
                                                                const Shard sh, const double* psi_tab, int tab_n) {
-  __shared__ double s_tab[2][3][kMaxCoarse];
+  __shared__ double s_tab[2][kMaxCoarse];
   __shared__ long long s_red[kThreadsB / 32];
   __shared__ int s_redi[3][kThreadsB / 32];
   const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
   for (int q = threadIdx.x; q < Bc; q += blockDim.x) {
-    s_tab[0][0][q] = q < Bc - 1 ? cx.split[q] : d_inf(); s_tab[0][1][q] = cx.clo[q]; s_tab[0][2][q] = cx.csc[q];
-    s_tab[1][0][q] = q < Bc - 1 ? cy.split[q] : d_inf(); s_tab[1][1][q] = cy.clo[q]; s_tab[1][2][q] = cy.csc[q];
+    s_tab[0][q] = q < Bc - 1 ? cx.split[q] : d_inf();
+    s_tab[1][q] = q < Bc - 1 ? cy.split[q] : d_inf();
   }
   __syncthreads();
-  const GridView gx{{s_tab[0][0], s_tab[0][1], s_tab[0][2], Bc}, cx.fg, cx.fval, cx.fstart};
-  const GridView gy{{s_tab[1][0], s_tab[1][1], s_tab[1][2], Bc}, cy.fg, cy.fval, cy.fstart};
+  const GridView gx{{s_tab[0], nullptr, nullptr, Bc}, cx.fg, cx.fval, cx.fstart};
+  const GridView gy{{s_tab[1], nullptr, nullptr, Bc}, cy.fg, cy.fval, cy.fstart};
   const long long s64 = (long long)blockIdx.x * kThreadsB + threadIdx.x;
   const int slot = (int)min(s64, n - 1);
   const int off = cx.boff[pr.pbkt[slot]];
@@ -781,8 +783,11 @@ __global__ void __launch_bounds__(kThreadsB) count_psi_kernel(const Col* cols, c
     const double e = pr.eps[slot];
     const double r = e - 1e-12;                                // _entropy_estimators.py:109
     const int row = pr.prow[slot];
-    const int nx = grid_count(gx, pr.pbkt[slot] / kSub, pr.px[slot], r);
-    const int ny = grid_count(gy, cy.bkt[row] / kSub, pr.py[slot], r);
+    const double vx = pr.px[slot], vy = pr.py[slot];
+    const CountPlan plx = count_plan(gx, pr.pbkt[slot], vx, r);
+    const CountPlan ply = count_plan(gy, cy.bkt[row], vy, r);
+    const int nx = count_run(gx, plx, vx, r);
+    const int ny = count_run(gy, ply, vy, r);
     if (pr.eps_row) pr.eps_row[row] = e;
     if (pr.nx_row) pr.nx_row[row] = nx;
     if (pr.ny_row) pr.ny_row[row] = ny;
@@ -845,10 +850,11 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 Plan make_plan(int64_t n, bool* ok) {
   Plan p;
   p.n = n;
-  // rows per bucket ~ 2 sqrt(n): a bucket should be about as wide in x as a typical k-th neighbour distance, which
+  // rows per bucket ~ 1.4 sqrt(n) (measured optimum): a bucket should be about as wide in x as a typical k-th neighbour distance, which
   // shrinks like 1 / sqrt(n) in two dimensions
-  int64_t rows = 256;
-  while (rows < kCoarseRows && rows * rows < 4 * n) rows += 64;
+  int64_t rows = 256, factor4 = 8;                            // factor4 / 4 = (rows / sqrt(n))^2
+  if (const char* e = getenv("EB2_K2_ROWS4")) factor4 = atoll(e);     // tuning knob
+  while (rows < kCoarseRows && rows * rows * 4 < factor4 * n) rows += 64;
   int64_t Bc = (n + rows - 1) / rows;
   if (Bc < 1) Bc = 1;
   bool fits = n >= 2 && n < (int64_t(1) << 30);
@@ -860,6 +866,7 @@ Plan make_plan(int64_t n, bool* ok) {
   p.NB = p.Bc * kSub;
   int64_t over = n / Bc;
   if (over > kOversample) over = kOversample;
+  while (over > 1 && over * Bc > 4096) --over;                 // the sample (over * Bc values) is ranked in shared memory
   if (over < 1) over = 1;
   p.over = static_cast<int>(over);
   if (ok) *ok = fits;
@@ -948,7 +955,7 @@ Prob carve_prob(char* base, const Plan& p, int k1t, int cx, int cy) {
 
 cudaError_t init() { return cudaSuccess; }      // (no kernel needs an opt-in shared-memory size at present)
 
-cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
+cudaError_t colgrid_buckets(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
   const int nb = static_cast<int>((p.n + kHistRows - 1) / kHistRows);
   const int S = p.Bc * p.over;
   sample_gather_kernel<<<dim3((S + kRankThreads - 1) / kRankThreads, ncol), kRankThreads, 0, s>>>(cols, p.n, S);
@@ -956,9 +963,19 @@ cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, in
   split_tables_kernel<<<ncol, kSplitThreads, 0, s>>>(cols, p.Bc, p.over, p.NB);
   bucket_hist_kernel<<<dim3(nb, ncol), kThreadsB, 0, s>>>(cols, p.n, p.Bc, p.NB);
   bucket_scatter_kernel<<<dim3(nb, ncol), kThreadsB, 0, s>>>(cols, p.n, p.NB);
-  fine_cells_kernel<<<dim3(p.NB, ncol), kThreadsB, 0, s>>>(cols, p.n, p.NB);
-  if (launches) *launches += 6;
+  if (launches) *launches += 5;
   return cudaGetLastError();
+}
+
+cudaError_t colgrid_cells(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
+  fine_cells_kernel<<<dim3(p.NB, ncol), kThreadsB, 0, s>>>(cols, p.n, p.NB);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches) {
+  const cudaError_t e = colgrid_buckets(cols, ncol, p, s, launches);
+  return e != cudaSuccess ? e : colgrid_cells(cols, ncol, p, s, launches);
 }
 
 cudaError_t layout(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches) {
@@ -969,7 +986,7 @@ cudaError_t layout(const Col* cols, const Prob* probs, int nprob, const Plan& p,
 
 cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, int k, const Shard& sh, int sm_count,
                 cudaStream_t s, int* launches) {
-  int near = 2;
+  int near = 3;
   if (const char* e = getenv("EB2_K2_NEAR")) near = atoi(e);       // tuning knob: buckets per side before a query is deferred
   const int grid = static_cast<int>((p.n + kThreadsB - 1) / kThreadsB);
   const int lgrid = nprob > 1 ? std::max(1, sm_count * 8 / nprob) : sm_count * 8;

@@ -33,10 +33,10 @@ namespace eb2 {
 namespace k2 {
 
 constexpr int kSub = 1;              // linear parts per quantile stretch (1: buckets are the quantile stretches themselves)
-constexpr int kMaxCoarse = 512;      // quantile stretches per column (at most)
+constexpr int kMaxCoarse = 1024;     // quantile stretches per column (at most)
 constexpr int kMaxBuckets = kSub * kMaxCoarse;
 constexpr int kCoarseRows = 2048;    // target rows per quantile stretch
-constexpr int kOversample = 8;       // sample values per quantile stretch
+constexpr int kOversample = 8;       // sample values per quantile stretch (at most; 4,096 samples in all)
 constexpr int kBucketCap = 8192;     // most rows a bucket may hold (cells are built by one CTA in shared memory)
 constexpr int kMaxCells = 4096;      // most cells per bucket
 constexpr int kFixedBits = 48;       // digamma terms are accumulated in units of 2^-48
@@ -124,6 +124,9 @@ cudaError_t init();       // opt-in shared memory sizes (once per device)
 
 // cols / probs: DEVICE arrays.  Launch counts are added to *launches.
 cudaError_t colgrid(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches);
+// ... in two steps: the bucket structure (all a layout / search needs of the x column) and the fine cells (counts only)
+cudaError_t colgrid_buckets(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches);
+cudaError_t colgrid_cells(const Col* cols, int ncol, const Plan& p, cudaStream_t s, int* launches);
 cudaError_t layout(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches);
 cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, int k, const Shard& sh, int sm_count,
                 cudaStream_t s, int* launches);

@@ -19,6 +19,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -92,7 +93,7 @@ DevShared g_shared[kMaxDev];
 
 struct Ctx {
   int dev = -1;
-  bool ready = false;
+  std::atomic<bool> ready{false};    // published with release order once every field below is set (get_ctx)
   std::mutex mu;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // second stream: work that can overlap the k-NN kernel (marginal sort)
@@ -143,9 +144,9 @@ Ctx& get_ctx(int dev_lane) {
   const int dev = dev_lane & 0xff, lane = (dev_lane >> 8) & 0xff;
   if (dev_lane < 0 || dev >= kMaxDev || lane >= kMaxLanes) throw CudaFail{cudaErrorInvalidDevice, "device index", __LINE__};
   Ctx& c = g_ctx[dev * kMaxLanes + lane];
-  if (c.ready) return c;
+  if (c.ready.load(std::memory_order_acquire)) return c;
   std::lock_guard<std::mutex> g(g_init_mu);
-  if (c.ready) return c;
+  if (c.ready.load(std::memory_order_acquire)) return c;
   int count = 0;
   CU(cudaGetDeviceCount(&count));
   if (dev >= count) throw CudaFail{cudaErrorInvalidDevice, "device index beyond cudaGetDeviceCount", __LINE__};
@@ -178,7 +179,7 @@ Ctx& get_ctx(int dev_lane) {
   CU(cudaMallocHost(reinterpret_cast<void**>(&c.pinned), c.pinned_cap));
   c.dev = dev;
   c.shared = &g_shared[dev];
-  c.ready = true;
+  c.ready.store(true, std::memory_order_release);
   return c;
 }
 
@@ -1259,7 +1260,7 @@ int eb2_shutdown(void) {
   std::lock_guard<std::mutex> g(g_init_mu);
   for (int d = 0; d < kMaxDev * kMaxLanes; ++d) {
     Ctx& c = g_ctx[d];
-    if (!c.ready) continue;
+    if (!c.ready.load(std::memory_order_acquire)) continue;
     std::lock_guard<std::mutex> g2(c.mu);
     cudaSetDevice(c.dev);
     cudaStreamSynchronize(c.stream);
@@ -1285,7 +1286,7 @@ int eb2_shutdown(void) {
     cudaStreamDestroy(c.stream);
     cudaFreeHost(c.pinned);
     c.pinned = nullptr;
-    c.ready = false;
+    c.ready.store(false, std::memory_order_release);
   }
   return EB2_OK;
 }
@@ -1330,20 +1331,26 @@ int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
 // One H2D copy of a row-major (n x ncols) block (row stride ld >= ncols elements) and a device-side
 // de-interleave into ncols cached columns: replaces ncols strided gathers on the host (pairwise_mi on an
 // (n, nvar) array spent more time transposing on the CPU than estimating on the GPU).
-int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* host, int64_t n, int64_t ld) {
-  if (!keys || !host || ncols <= 0 || n <= 0 || ld < ncols) return fail(EB2_ERR_ARG, "eb2_cache_put_block: bad argument");
+static int cache_put_block_impl(int dev, const uint64_t* keys, int ncols, const double* src, int64_t n, int64_t ld, bool on_device) {
+  if (!keys || !src || ncols <= 0 || n <= 0 || ld < ncols) return fail(EB2_ERR_ARG, "eb2_cache_put_block: bad argument");
   for (int j = 0; j < ncols; ++j)
     if (keys[j] == 0) return fail(EB2_ERR_ARG, "eb2_cache_put_block: key 0 is reserved");
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CU(cudaSetDevice(c.dev));
     const size_t count = static_cast<size_t>(n) * ncols;
-    double* block = s.dev<double>(count);
-    if (ld == ncols)
-      CU(cudaMemcpyAsync(block, host, sizeof(double) * count, cudaMemcpyHostToDevice, c.stream));
-    else
-      CU(cudaMemcpy2DAsync(block, sizeof(double) * ncols, host, sizeof(double) * ld, sizeof(double) * ncols,
-                           static_cast<size_t>(n), cudaMemcpyHostToDevice, c.stream));
+    const double* block = src;
+    int64_t bld = ld;
+    if (!on_device) {
+      double* staged = s.dev<double>(count);
+      if (ld == ncols)
+        CU(cudaMemcpyAsync(staged, src, sizeof(double) * count, cudaMemcpyHostToDevice, c.stream));
+      else
+        CU(cudaMemcpy2DAsync(staged, sizeof(double) * ncols, src, sizeof(double) * ld, sizeof(double) * ncols,
+                             static_cast<size_t>(n), cudaMemcpyHostToDevice, c.stream));
+      block = staged;
+      bld = ncols;
+    }
     std::vector<double*> cols(ncols, nullptr);
     try {
       for (int j = 0; j < ncols; ++j)
@@ -1352,9 +1359,9 @@ int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* 
       std::memcpy(table_h, cols.data(), sizeof(double*) * ncols);
       double** table_d = s.dev<double*>(ncols);
       CU(cudaMemcpyAsync(table_d, table_h, sizeof(double*) * ncols, cudaMemcpyHostToDevice, c.stream));
-      deinterleave_kernel<<<dim3(cdiv(n, 32), cdiv(ncols, 32)), dim3(32, 8), 0, c.stream>>>(block, n, ncols, table_d);
+      deinterleave_kernel<<<dim3(cdiv(n, 32), cdiv(ncols, 32)), dim3(32, 8), 0, c.stream>>>(block, n, ncols, bld, table_d);
       CU(cudaGetLastError());
-      CU(cudaStreamSynchronize(c.stream));      // the caller may reuse `host` right away
+      CU(cudaStreamSynchronize(c.stream));      // the caller may reuse the source right away
     } catch (...) {
       for (double* p : cols)
         if (p) cudaFreeAsync(p, c.stream);
@@ -1372,6 +1379,16 @@ int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* 
     }
     return EB2_OK;
   });
+}
+
+int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* host, int64_t n, int64_t ld) {
+  return cache_put_block_impl(dev, keys, ncols, host, n, ld, false);
+}
+
+// the same from a block that already is in device memory on `dev` (e.g. row slices uploaded by the ranks of a job and
+// all-gathered over NVLink: every rank pays for 1/G of the host-to-device copy)
+int eb2_cache_put_block_dev(int dev, const uint64_t* keys, int ncols, const double* dev_block, int64_t n, int64_t ld) {
+  return cache_put_block_impl(dev, keys, ncols, dev_block, n, ld, true);
 }
 
 int eb2_cache_drop(int dev, uint64_t key) {
@@ -1514,11 +1531,22 @@ double* run_k2(Scratch& s, const k2::Plan& plan, const double* raw, int64_t n, i
   k2_setup_kernel<<<1, 1, 0, st>>>(hc0, hc1, hp, dcols, dprob);
   s.launches++;
   const k2::Shard sh{row_lo, row_hi};
-  CU(k2::colgrid(dcols, 2, plan, st, &s.launches));
+  // the search needs the bucket structure of x only: the y column's grid and the fine cells of both columns (what the
+  // marginal counts read) are built on the second stream while layout and search run
+  s.used_side = true;
+  CU(cudaEventRecord(c.fork, st));
+  CU(cudaStreamWaitEvent(c.side, c.fork, 0));
+  CU(k2::colgrid_buckets(dcols, 1, plan, st, &s.launches));
+  CU(k2::colgrid_buckets(dcols + 1, 1, plan, c.side, &s.launches));
+  CU(cudaEventRecord(c.fork, st));                  // (re-used: x buckets done)
+  CU(cudaStreamWaitEvent(c.side, c.fork, 0));
+  CU(k2::colgrid_cells(dcols, 2, plan, c.side, &s.launches));
+  CU(cudaEventRecord(c.join, c.side));
   CU(k2::layout(dcols, dprob, 1, plan, st, &s.launches));
   mark(s, 1);
   CU(k2::knn(dcols, dprob, 1, plan, k, sh, c.sm_count, st, &s.launches));
   mark(s, 2);
+  side_join(s);
   CU(k2::count_psi(dcols, dprob, 1, plan, sh, c.psi_tab, kPsiTab, st, &s.launches));
   mark(s, 3);
   CU(k2::finalize(dcols, dprob, 1, plan, st, &s.launches));

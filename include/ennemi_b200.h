@@ -159,6 +159,9 @@ EB2_API int eb2_cache_drop(int dev, uint64_t key);                              
  * Replaces the per-column strided gathers the host would otherwise do for the (n, nvar) arrays the reference's
  * pairwise_mi / estimate_mi take (ennemi/_driver.py:477-483, 703-707 slice them column by column). */
 EB2_API int eb2_cache_put_block(int dev, const uint64_t* keys, int ncols, const double* host, int64_t n, int64_t ld);
+/* ... from a block that already is in DEVICE memory on `dev` (multi-GPU jobs: every rank uploads 1/G of the rows and
+ * the slices are all-gathered over NVLink before this call) */
+EB2_API int eb2_cache_put_block_dev(int dev, const uint64_t* keys, int ncols, const double* dev_block, int64_t n, int64_t ld);
 
 /* mean and standard deviation (ddof = 0) of the window column[key][off + i*stride], i in [0, n), computed on the
  * device with NumPy's pairwise-summation association, i.e. the same bits as ndarray.mean() / ndarray.std()
