@@ -302,6 +302,17 @@ class ColsTask:
         mean = NaN) instead of asking for them first."""
         lo_pad, hi_pad = max(self.hi, 0), min(self.lo, 0)            # as _align.lagged_windows
         n_tot = self.n_total
+        if not in_call_stats and not self.zkeys and isinstance(self.lag, (int, np.integer)):
+            # both variables already described in these roles by an earlier task of the call (pairwise_mi asks for
+            # each column 63 times): two dictionary look-ups instead of the work below
+            n_fast = n_tot + hi_pad - lo_pad
+            ordinal_fast = _devices.ordinal(dev)
+            hx = self.store.cached_desc(((self.xkey, int(lo_pad - self.lag), n_fast), (), ordinal_fast, self.preprocess))
+            if hx is not None:
+                hy = self.store.cached_desc(((self.ykey, int(lo_pad), n_fast), ((n_fast,),) if hx[1] else (), ordinal_fast,
+                                             self.preprocess))
+                if hy is not None and n_fast > self.k:
+                    return [hx[0], hy[0]], n_fast
         xs = self.xview[lo_pad - self.lag: n_tot - self.lag + hi_pad]   # views: non-integer lags raise here
         ys = self.yview[lo_pad: n_tot + hi_pad]
         n = len(ys)
@@ -360,12 +371,16 @@ class ColsTask:
                 return lambda: _native.cache_stats(key, off, n, dev=dev)
             return lambda: window_stats(view)
 
-        if n >= OVERLAP_MIN_ROWS and self.preprocess and not in_call_stats and self.store.missing(dev, self.xkey, self.ykey):
-            # large first-time windows: the two uploads (and statistics) run side by side on two stream lanes
+        if n >= OVERLAP_MIN_ROWS and self.store.missing(dev, self.xkey, self.ykey):
+            # large first-time windows: the two uploads (and statistics, unless the library call computes them itself)
+            # run side by side on two stream lanes - from pageable memory each is bound by one thread's memcpy
+            want_stats = self.preprocess and not in_call_stats
+
             def side(key, off, view, lane_dev):
                 self.store.ensure(lane_dev, key)
-                self.store.stats((key, off, n), (lambda: _native.cache_stats(key, off, n, dev=lane_dev)) if device_stats
-                                 else (lambda: window_stats(view)))
+                if want_stats:
+                    self.store.stats((key, off, n), (lambda: _native.cache_stats(key, off, n, dev=lane_dev)) if device_stats
+                                     else (lambda: window_stats(view)))
             other = _devices.with_lane(dev, ((dev >> 8) + 1) % 4)
             fut = _helper_pool().submit(side, self.ykey, y_off, ys, other)
             side(self.xkey, x_off, xs, dev)

@@ -35,7 +35,7 @@ EXPORTS = (
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
-    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs", "eb2_last_pipeline", "eb2_cache_put_block_dev",
+    "eb2_cache_put_block", "eb2_cache_stats_many", "eb2_ksg_mi_pairs", "eb2_last_pipeline", "eb2_cache_put_block_dev", "eb2_sharded_ksg_mi",
 )
 
 _lib = None
@@ -93,6 +93,7 @@ def load():
         lib.eb2_cache_drop.argtypes = [_int, ctypes.c_uint64]
         lib.eb2_cache_put_block.argtypes = [_int, _vp, _int, _vp, _i64, _i64]
         lib.eb2_cache_put_block_dev.argtypes = [_int, _vp, _int, _vp, _i64, _i64]
+        lib.eb2_sharded_ksg_mi.argtypes = [_int, _vp, _i64, _int, _u32, _c_dp]
         lib.eb2_cache_stats_many.argtypes = [_int, _vp, _vp, _int, _i64, _i64, _vp, _vp]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
@@ -164,6 +165,16 @@ def ksg_mi(coords: np.ndarray, k: int, dev: int = 0, flags: int = 0, details: bo
     if rc:
         _raise(rc)
     return (value.value, {"eps": eps, "nx": nx, "ny": ny}) if details else value.value
+
+
+def sharded_ksg_mi(coords: np.ndarray, k: int, ngpu: int, flags: int = 0) -> float:
+    """One estimate with its query rows sharded over the first ``ngpu`` GPUs of the box, from this one process
+    (``eb2_sharded_ksg_mi``); bit-identical for every ``ngpu``."""
+    value = ctypes.c_double()
+    rc = load().eb2_sharded_ksg_mi(ngpu, coords.ctypes.data, coords.shape[1], k, flags, ctypes.byref(value))
+    if rc:
+        _raise(rc)
+    return value.value
 
 
 def ksg_mi_rows(coords_ptr: int, n: int, k: int, row_lo: int, row_hi: int, dev: int = 0, flags: int = 0) -> np.ndarray:

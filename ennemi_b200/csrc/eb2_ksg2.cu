@@ -498,7 +498,12 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
   const int lane = threadIdx.x & 31;
-  const long long s64 = (long long)blockIdx.x * kThreadsB + threadIdx.x;
+  // CTAs are dispatched in index order: take the slots from both ends of x inwards (even CTAs from the front, odd ones
+  // from the back) - the outermost buckets hold the sparse tails, whose queries search the widest windows, and must not
+  // be the last ones to start
+  const unsigned nblk = gridDim.x;
+  const unsigned blk = (blockIdx.x & 1u) ? nblk - 1u - (blockIdx.x >> 1) : (blockIdx.x >> 1);
+  const long long s64 = (long long)blk * kThreadsB + threadIdx.x;
   const int slot = (int)min(s64, n - 1);
   const int b = pr.pbkt[slot];
   const int off = cx.boff[b];

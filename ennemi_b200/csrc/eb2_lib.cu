@@ -30,6 +30,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -101,6 +102,8 @@ struct Ctx {
   cudaEvent_t ev[kNumEvents] = {};
   int sm_count = 148;
   char* pinned = nullptr;   // host staging: tile tables up, results down
+  char* bounce = nullptr;   // page-locked bounce buffer for uploads from pageable memory (kBounceSlots x kBounceBytes)
+  cudaEvent_t bounce_ev[4] = {};
   size_t pinned_cap = 0;
   double last_ms[5] = {0, 0, 0, 0, 0};
   int last_launches = 0;
@@ -181,6 +184,40 @@ Ctx& get_ctx(int dev_lane) {
   c.shared = &g_shared[dev];
   c.ready.store(true, std::memory_order_release);
   return c;
+}
+
+
+// Host -> device copy of a large array on the lane's stream, complete on return.  Pageable memory is what users pass
+// (NumPy arrays): cudaMemcpyAsync stages it internally at ~8 GB/s.  Here the calling thread copies 1 MiB pieces into a
+// page-locked ring while the DMA engine moves the previous ones, which runs at the host's memcpy speed (and two lanes
+// uploading two variables side by side double it).
+constexpr size_t kBounceBytes = size_t(1) << 20;
+constexpr int kBounceSlots = 4;
+void upload(Ctx& c, void* dst, const void* src, size_t bytes) {
+  cudaPointerAttributes attr;
+  bool pageable = true;
+  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+  else cudaGetLastError();
+  if (!pageable || bytes < 2 * kBounceBytes || getenv("EB2_NO_BOUNCE")) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    return;
+  }
+  if (!c.bounce) {
+    CU(cudaMallocHost(reinterpret_cast<void**>(&c.bounce), kBounceBytes * kBounceSlots));
+    for (auto& e : c.bounce_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  size_t done = 0;
+  for (int i = 0; done < bytes; ++i) {
+    const int slot = i % kBounceSlots;
+    const size_t len = std::min(kBounceBytes, bytes - done);
+    if (i >= kBounceSlots) CU(cudaEventSynchronize(c.bounce_ev[slot]));      // the slot's previous piece has left
+    std::memcpy(c.bounce + slot * kBounceBytes, static_cast<const char*>(src) + done, len);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + done, c.bounce + slot * kBounceBytes, len, cudaMemcpyHostToDevice, c.stream));
+    CU(cudaEventRecord(c.bounce_ev[slot], c.stream));
+    done += len;
+  }
+  CU(cudaStreamSynchronize(c.stream));
 }
 
 // Per-call scratch: stream-ordered allocations, released when the call ends.
@@ -875,7 +912,8 @@ const double* stage_input(Scratch& s, const Input& in, int d, int64_t n, int* no
     raw = dv;
   } else if (!(in.flags & EB2_FLAG_DEVICE_INPUT)) {
     double* dv = s.dev<double>(static_cast<size_t>(total));
-    CU(cudaMemcpyAsync(dv, in.coords, sizeof(double) * total, cudaMemcpyHostToDevice, s.c.stream));
+    if (s.capture) CU(cudaMemcpyAsync(dv, in.coords, sizeof(double) * total, cudaMemcpyHostToDevice, s.c.stream));
+    else upload(s.c, dv, in.coords, sizeof(double) * total);
     raw = dv;
   }
   if (check_finite) {
@@ -1286,6 +1324,11 @@ int eb2_shutdown(void) {
     cudaStreamDestroy(c.stream);
     cudaFreeHost(c.pinned);
     c.pinned = nullptr;
+    if (c.bounce) {
+      cudaFreeHost(c.bounce);
+      c.bounce = nullptr;
+      for (auto& e : c.bounce_ev) cudaEventDestroy(e);
+    }
     c.ready.store(false, std::memory_order_release);
   }
   return EB2_OK;
@@ -1314,9 +1357,12 @@ int eb2_cache_put(int dev, uint64_t key, const double* host, int64_t n) {
     CU(cudaSetDevice(c.dev));
     double* p = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(double) * n, c.stream));   // from the cached pool
-    cudaError_t e = cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, c.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);     // the caller may reuse `host` right away
-    if (e != cudaSuccess) { cudaFreeAsync(p, c.stream); throw CudaFail{e, "eb2_cache_put copy", __LINE__}; }
+    try {
+      upload(c, p, host, sizeof(double) * n);                       // complete on return: the caller may reuse `host`
+    } catch (...) {
+      cudaFreeAsync(p, c.stream);
+      throw;
+    }
     std::lock_guard<std::mutex> cache_guard(c.shared->mu);
     auto it = c.shared->cache.find(key);
     if (it != c.shared->cache.end()) {
@@ -1344,7 +1390,7 @@ static int cache_put_block_impl(int dev, const uint64_t* keys, int ncols, const 
     if (!on_device) {
       double* staged = s.dev<double>(count);
       if (ld == ncols)
-        CU(cudaMemcpyAsync(staged, src, sizeof(double) * count, cudaMemcpyHostToDevice, c.stream));
+        upload(c, staged, src, sizeof(double) * count);
       else
         CU(cudaMemcpy2DAsync(staged, sizeof(double) * ncols, src, sizeof(double) * ld, sizeof(double) * ncols,
                              static_cast<size_t>(n), cudaMemcpyHostToDevice, c.stream));
@@ -1755,6 +1801,38 @@ int eb2_ksg_mi(int dev, const double* coords, int64_t n, int k, uint32_t flags, 
   return eb2_ksg_mi_finish(partial, n, k, value);
 }
 
+
+// ---- configs[1] from ONE process: the query rows of a single estimate sharded over the GPUs of the box -----------------
+// (the multi-process form of the same - one rank per GPU, torch.distributed, NCCL all-reduce of the partial blocks - is
+// ennemi_b200/distributed.py).  Every GPU receives the point set, builds its grid, searches and counts the buckets of its
+// shard; the partial blocks are summed here on the host.  Their digamma sums are exact integers (EB2_P_FIX0), so the
+// value is bit-identical for every ngpu.
+int eb2_sharded_ksg_mi(int ngpu, const double* coords, int64_t n, int k, uint32_t flags, double* value) {
+  if (int rc0 = check_common(coords, n, 2, k)) return rc0;
+  if (!value) return fail(EB2_ERR_ARG, "value is NULL");
+  if (flags & EB2_FLAG_DEVICE_INPUT) return fail(EB2_ERR_ARG, "eb2_sharded_ksg_mi takes host buffers only");
+  const int avail = eb2_device_count();
+  if (ngpu < 1 || ngpu > avail) return fail(EB2_ERR_ARG, "ngpu = %d, but %d CUDA device(s) are usable", ngpu, avail);
+  std::vector<std::vector<double>> parts(ngpu, std::vector<double>(EB2_P_LEN, 0.0));
+  std::vector<int> rcs(ngpu, 0);
+  std::vector<std::string> errs(ngpu);
+  std::vector<int> dflags(ngpu, 0);
+  auto work = [&](int g) {
+    const int64_t lo = n * g / ngpu, hi = n * (g + 1) / ngpu;
+    rcs[g] = eb2_ksg_mi_rows(g, coords, n, k, flags, lo, hi, parts[g].data(), nullptr, nullptr, nullptr);
+    if (rcs[g]) { errs[g] = g_err; dflags[g] = g_data_flags; }       // (both are thread-local)
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < ngpu; ++g) threads.emplace_back(work, g);
+  work(0);
+  for (auto& t : threads) t.join();
+  for (int g = 0; g < ngpu; ++g)
+    if (rcs[g]) { g_err = errs[g]; g_data_flags = dflags[g]; return rcs[g]; }
+  std::vector<double> total(EB2_P_LEN, 0.0);
+  for (int g = 0; g < ngpu; ++g)
+    for (int i = 0; i < EB2_P_LEN; ++i) total[i] += parts[g][i];
+  return eb2_ksg_mi_finish(total.data(), n, k, value);
+}
 
 // ---- a7 for pairwise_mi: all pairs of a set of prepared variables in one call -------------------------------------
 // (the reference builds the same task list at ennemi/_driver.py:703-707 and maps it over a thread pool, :736-785).

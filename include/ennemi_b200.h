@@ -197,6 +197,12 @@ EB2_API int eb2_last_data_flags(void);
 EB2_API int eb2_mi_cols_batch(int dev, const eb2_col_t* cols, int64_t ntasks, int c, int64_t n, int k, uint32_t flags,
                               double* values, int* status);
 
+/* BASELINE.json configs[1] from ONE process: a single estimate with its query rows sharded over the first `ngpu` GPUs
+ * of the box (host buffers; every GPU receives the point set).  The partial blocks are summed on the host; their
+ * digamma sums are exact integers, so the value is bit-identical for every ngpu.  The one-process-per-GPU form (NCCL
+ * all-reduce of the same partial blocks) is ennemi_b200/distributed.py::sharded_ksg_mi. */
+EB2_API int eb2_sharded_ksg_mi(int ngpu, const double* coords, int64_t n, int k, uint32_t flags, double* value);
+
 /* a7 for pairwise_mi (the task list of ennemi/_driver.py:703-707 in ONE call): npairs bivariate estimates over a set
  * of nvar prepared variables; pair t is (x = cols[pairs[2t]], y = cols[pairs[2t+1]]).  Every variable is rescaled and
  * sorted once, the pairs run through the estimator in batches (one launch per stage for a whole batch).  values[t] /

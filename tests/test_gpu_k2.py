@@ -114,6 +114,19 @@ def test_value_is_independent_of_sharding_and_order():
         assert nat.ksg_mi_finish(total, n, 3) == whole, cuts
 
 
+def test_single_process_sharding_over_the_visible_gpus():
+    """eb2_sharded_ksg_mi: same bits for every number of GPUs (here: as many as the box shows, at least one)."""
+    rng = np.random.default_rng(2)
+    n = 300_000
+    d = rng.multivariate_normal([0, 0], [[1, 0.3], [0.3, 1]], size=n)
+    co = nat.pack_coords([d[:, 0], d[:, 1]])
+    whole = nat.ksg_mi(co, 3)
+    for g in range(1, min(nat.device_count(), 8) + 1):
+        assert nat.sharded_ksg_mi(co, 3, g) == whole, g
+    with pytest.raises(ValueError):
+        nat.sharded_ksg_mi(co, 3, nat.device_count() + 1)
+
+
 def test_all_pairs_call_matches_single_estimates():
     """eb2_ksg_mi_pairs (every pair of pairwise_mi in one call, batched per stage) against one estimate per pair, and a
     few pairs against the oracle; a NaN column fails only the pairs that use it."""
