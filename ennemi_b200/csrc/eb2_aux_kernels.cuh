@@ -75,6 +75,51 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// (1') k-th neighbour distance in ONE dimension (Ross within a class, :194; 1-D entropy, :39): inside a segment the
+//      coordinate ascends, so the k nearest neighbours of a row are among its k predecessors and k successors and
+//      their distances ascend with the offset on either side (rounded subtraction is monotone): a two-pointer merge
+//      of the two sides yields the k smallest distances in order.  Exactly the values the all-pairs kernel would
+//      select (|fl(x_i - x_j)|, self included at 0; inf when the segment holds fewer than k + 1 rows).
+// ----------------------------------------------------------------------------------------------
+struct Knn1dArgs {
+  const double* x;        // the sorted coordinate row of the padded point set
+  const Tile* tiles;      // q_lo/q_n: query slots; c_lo/c_len: their segment
+  int ntiles;
+  int k;
+  double* eps;            // out per query slot
+  unsigned long long* pairs;
+};
+
+__global__ void __launch_bounds__(kThreads) knn1d_kernel(const Knn1dArgs a) {
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = a.tiles[tile_id];
+    const double* seg = a.x + tile.c_lo;
+    for (int qi = threadIdx.x; qi < tile.q_n; qi += kThreads) {
+      const int slot = tile.q_lo + qi;
+      const int rel = slot - tile.c_lo;
+      const double xq = seg[rel];
+      int l = rel - 1, r = rel + 1;
+      double dl = l >= 0 ? xq - seg[l] : kInf, dr = r < tile.c_len ? seg[r] - xq : kInf;
+      double cur = 0.0;                                   // the row itself
+      for (int step = 0; step < a.k; ++step) {
+        if (dl <= dr) {
+          cur = dl;
+          --l;
+          dl = l >= 0 ? xq - seg[l] : kInf;
+        } else {
+          cur = dr;
+          ++r;
+          dr = r < tile.c_len ? seg[r] - xq : kInf;
+        }
+      }
+      a.eps[slot] = cur;
+    }
+    if (threadIdx.x == 0 && a.pairs) atomicAdd(a.pairs, (unsigned long long)tile.q_n * (unsigned long long)(2 * a.k + 1));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // (3) digamma terms + deterministic reduction
 // ----------------------------------------------------------------------------------------------
 enum PsiMode { PSI_A = 1, PSI_AB = 2, PSI_AB_MINUS_C = 3, LOG_DIST = 4 };

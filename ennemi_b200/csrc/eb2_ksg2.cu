@@ -27,7 +27,6 @@ constexpr int kThreadsB = 256;                 // threads per CTA everywhere els
 constexpr double kSlack = 8.881784197001252e-16;   // 2^-50
 
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
-__device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // floor((v - lo) * sc) clamped to [0, ncell - 1]: monotone non-decreasing in v (rounded subtraction, multiplication
 // by a non-negative scale, truncation and clamping all are).  The one function cells are built AND queried with.
@@ -357,74 +356,7 @@ __global__ void __launch_bounds__(kLayoutThreads, 2) layout_kernel(const Col* co
 }
 
 // ---- knn ---------------------------------------------------------------------------------------------------------------
-constexpr int kHitCap = 8;            // slots a thread notes down before it folds them into its list
-
-// Slots [a, e) against one query.  The scan itself is branch-free per group of four (the eight loads of a group are
-// independent and in flight together): slots that pass the exact test against the threshold of the moment are only
-// NOTED (their index, in a per-thread strip of shared memory); the noted slots are folded into the sorted list when the
-// strip fills up and at the end, re-tested against the threshold as it stands then.  A warp's lanes hit at different
-// slots: noting keeps them in step where inserting on the spot would serialise them.
-template <int K1T, bool GATED>
-__device__ __forceinline__ void scan_slots(const double* __restrict__ px, const double* __restrict__ py, int a, int e,
-                                           double qx, double qy, double (&best)[K1T], double& thr, unsigned long long& np,
-                                           double gate, int* hit) {
-  if (e > a) np += (unsigned long long)(e - a);
-  constexpr int G = 4;
-  int cnt = 0;
-  auto fold = [&]() {
-#pragma unroll 1
-    for (int i = 0; i < cnt; ++i) {
-      const int t = hit[i * kThreadsB];
-      const double xv = px[t], yv = py[t];
-      if (fabs(qx - xv) < thr && fabs(qy - yv) < thr) {
-        topk_insert<K1T>(best, fmax(fabs(qx - xv), fabs(qy - yv)));
-        thr = GATED ? fmin(best[K1T - 1], gate) : best[K1T - 1];
-      }
-    }
-    cnt = 0;
-  };
-#pragma unroll 1
-  for (int s = a; s < e; s += G) {
-    double xv[G], yv[G];
-#pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const int t = min(s + u, e - 1);             // the last group repeats its final slot; repeats are masked below
-      xv[u] = px[t];
-      yv[u] = py[t];
-    }
-#pragma unroll
-    for (int u = 0; u < G; ++u) {
-      const bool pass = s + u < e && fabs(qx - xv[u]) < thr && fabs(qy - yv[u]) < thr;
-      if (pass) hit[cnt * kThreadsB] = s + u;
-      cnt += (int)pass;
-    }
-    if (cnt > kHitCap - G) fold();
-  }
-  fold();
-}
-
-// every row of x-bucket [off, off + len) whose y can lie within thr of qy (the cells the widened window touches);
-// slots [skip_a, skip_e) have been examined already
-template <int K1T, bool GATED>
-__device__ __forceinline__ void visit_bucket(const Prob& pr, int off, int len, double ymin, double sc, double qx, double qy,
-                                             double (&best)[K1T], double& thr, unsigned long long& np, int skip_a, int skip_e,
-                                             double gate, int* hit) {
-  int a = off, e = off + len;
-  if (thr < d_inf()) {
-    const int F = min(len, kMaxCells);
-    const double lo_v = (qy - thr) - (fabs(qy) + thr) * kSlack;
-    const double hi_v = (qy + thr) + (fabs(qy) + thr) * kSlack;
-    const int f_lo = lin_cell(lo_v, ymin, sc, F), f_hi = lin_cell(hi_v, ymin, sc, F);
-    a = pr.cstart[off + f_lo];
-    if (f_hi + 1 < F) e = pr.cstart[off + f_hi + 1];
-  }
-  if (skip_a < skip_e) {
-    scan_slots<K1T, GATED>(pr.px, pr.py, a, min(e, skip_a), qx, qy, best, thr, np, gate, hit);
-    scan_slots<K1T, GATED>(pr.px, pr.py, max(a, skip_e), e, qx, qy, best, thr, np, gate, hit);
-  } else {
-    scan_slots<K1T, GATED>(pr.px, pr.py, a, e, qx, qy, best, thr, np, gate, hit);
-  }
-}
+constexpr int kHeavy = 64;            // windows of more slots than this are scanned by a warp (leftover kernel), not a thread
 
 // window of x-bucket [off, off + len) whose y can lie within thr of qy: the slots of the cells the widened window touches
 __device__ __forceinline__ void bucket_window(const Prob& pr, int off, int len, double ymin, double sc, double qy, double thr,
@@ -536,24 +468,37 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
   for (int t = 0; t < K1T; ++t) best[t] = d[t];
   double thr = best[K1T - 1];
   if (valid) np += (unsigned long long)(se - sa);
+  // A window of more than kHeavy slots (a query in a sparse region: its k-th distance covers a good part of a bucket) is
+  // not walked by one thread: the query goes to the leftover kernel from that bucket on, where a warp scans it.
+  int rstart = NB, lend = 0, skip_a = -16;
+  bool heavy = false;
   // 2. the rest of the home bucket
   {
     int a = 0, e = 0;
     if (valid) bucket_window(pr, off, len, pr.bymin[b], pr.bysc[b], qy, thr, a, e);
+    if (e - a > kHeavy) {
+      heavy = true;
+      rstart = b; lend = b; skip_a = sa;
+      a = e = 0;
+    }
     scan_range<K1T, true>(px, py, a, e, qx, qy, best, thr, np, sa, se);
   }
   // 3. outwards
-  int rstart = NB, lend = 0;
   {
-    bool more = valid;
+    bool more = valid && !heavy;
     int j = b + 1;
     for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
       int a = 0, e = 0;
       if (more) {
         int lj = 0;
         while (j < NB && (lj = cx.count[j]) == 0) ++j;
-        if (j >= NB || (cx.vlo[j] - qx) >= thr) more = false;
-        else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); ++j; }
+        if (j >= NB || (cx.vlo[j] - qx) >= thr) {
+          more = false;
+        } else {
+          bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e);
+          if (e - a > kHeavy) { rstart = j; more = false; a = e = 0; }
+          else ++j;
+        }
       }
       scan_range<K1T, false>(px, py, a, e, qx, qy, best, thr, np);
     }
@@ -563,15 +508,20 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
     }
   }
   {
-    bool more = valid;
+    bool more = valid && !heavy;
     int j = b - 1;
     for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
       int a = 0, e = 0;
       if (more) {
         int lj = 0;
         while (j >= 0 && (lj = cx.count[j]) == 0) --j;
-        if (j < 0 || (qx - cx.vhi[j]) >= thr) more = false;
-        else { bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e); --j; }
+        if (j < 0 || (qx - cx.vhi[j]) >= thr) {
+          more = false;
+        } else {
+          bucket_window(pr, cx.boff[j], lj, pr.bymin[j], pr.bysc[j], qy, thr, a, e);
+          if (e - a > kHeavy) { lend = j + 1; more = false; a = e = 0; }
+          else --j;
+        }
       }
       scan_range<K1T, false>(px, py, a, e, qx, qy, best, thr, np);
     }
@@ -602,6 +552,7 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
           int a, e;
           bucket_window(pr, cx.boff[jj], lj, pr.bymin[jj], pr.bysc[jj], qy, thr, a, e);
           for (int s = a; s < e; ++s) {
+            if (s >= skip_a && s < skip_a + 8) continue;
             const double xh = px[s], yh = py[s];
             if (fabs(qx - xh) < thr && fabs(qy - yh) < thr) { topk_insert<K1T>(best, fmax(fabs(qx - xh), fabs(qy - yh))); thr = best[K1T - 1]; }
           }
@@ -627,7 +578,7 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
     pr.eps[slot] = r;
     if (my_e >= 0) {
       LeftEnt le;
-      le.slot = slot; le.rstart = rstart; le.lend = lend;
+      le.slot = slot; le.rstart = rstart; le.lend = lend; le.skip_a = skip_a;
       pr.left[my_e] = le;
 #pragma unroll
       for (int t = 0; t < K1T; ++t) pr.left_best[(long long)my_e * K1T + t] = best[t];
@@ -638,11 +589,13 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
   if (lane == 0 && np) atomicAdd(reinterpret_cast<unsigned long long*>(pr.out + 4), np);
 }
 
-// ---- leftover: one warp finishes one deferred query, its remaining buckets dealt to the lanes ------------------------
+// ---- leftover: one warp finishes one deferred query --------------------------------------------------------------------
+// Its remaining buckets are dealt to the lanes, 32 at a time: every lane works out the window of ITS bucket (cell
+// arithmetic, two table loads) and walks it if it is short; long windows (sparse regions: a good part of a bucket) are
+// then scanned by the whole warp, lanes striding over the slots.  Private lists per lane, gated by the k-th distance the
+// search kernel had reached; one merge across the lanes at the end.
 template <int K1T>
 __global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, const Prob* probs, int NB, int k) {
-  __shared__ int s_hit[kHitCap * kThreadsB];
-  int* hit = s_hit + threadIdx.x;
   const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
@@ -650,31 +603,56 @@ __global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, c
   const unsigned nent = *pr.left_count;
   const double kInf = d_inf();
   const int k1 = k + 1;
+  const double* __restrict__ px = pr.px;
+  const double* __restrict__ py = pr.py;
   unsigned long long np = 0;
   for (unsigned e = blockIdx.x * (kThreadsB / 32) + warp; e < nent; e += gridDim.x * (kThreadsB / 32)) {
     const LeftEnt le = pr.left[e];
-    const double qx = pr.px[le.slot], qy = pr.py[le.slot];
+    const double qx = px[le.slot], qy = py[le.slot];
     const double gate = pr.left_best[(long long)e * K1T + (K1T - 1)];      // current k-th distance: upper bound of eps
+    const int skip_a = le.skip_a, skip_e = le.skip_a + 8;
     double best[K1T];
 #pragma unroll
     for (int t = 0; t < K1T; ++t) best[t] = kInf;
     double thr = gate;
+    auto test = [&](int s) {
+      if (s >= skip_a && s < skip_e) return;                               // a seed: already in the list left behind
+      const double dx = fabs(qx - px[s]), dy = fabs(qy - py[s]);
+      if (dx < thr && dy < thr) {
+        topk_insert<K1T>(best, fmax(dx, dy));
+        thr = fmin(best[K1T - 1], gate);
+      }
+    };
+    // one round: lane's bucket j (needed or not) -> short windows per lane, long ones by the warp
+    auto round = [&](int j, bool needed) {
+      int a = 0, en = 0;
+      if (needed) bucket_window(pr, cx.boff[j], cx.count[j], pr.bymin[j], pr.bysc[j], qy, thr, a, en);
+      const bool big = en - a > kHeavy;
+      if (!big) {
+        for (int s = a; s < en; ++s) test(s);
+        if (en > a) np += (unsigned long long)(en - a);
+      }
+      unsigned todo = __ballot_sync(kFull, big);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int aa = __shfl_sync(kFull, a, src), ee = __shfl_sync(kFull, en, src);
+        for (int s = aa + lane; s < ee; s += 32) test(s);
+        if (lane == 0) np += (unsigned long long)(ee - aa);
+      }
+    };
     for (int j0 = le.rstart; j0 < NB; j0 += 32) {
       const int j = j0 + lane;
       const int len = j < NB ? cx.count[j] : 0;
       const bool fail = len > 0 && (cx.vlo[j] - qx) >= gate;               // monotone: every bucket further right fails too
-      if (len > 0 && !fail) {
-        visit_bucket<K1T, true>(pr, cx.boff[j], len, pr.bymin[j], pr.bysc[j], qx, qy, best, thr, np, 0, 0, gate, hit);
-      }
+      round(j, len > 0 && !fail);
       if (__any_sync(kFull, fail || j >= NB)) break;
     }
     for (int j0 = le.lend - 1; j0 >= 0; j0 -= 32) {
       const int j = j0 - lane;
       const int len = j >= 0 ? cx.count[j] : 0;
       const bool fail = len > 0 && (qx - cx.vhi[j]) >= gate;
-      if (len > 0 && !fail) {
-        visit_bucket<K1T, true>(pr, cx.boff[j], len, pr.bymin[j], pr.bysc[j], qx, qy, best, thr, np, 0, 0, gate, hit);
-      }
+      round(j, len > 0 && !fail);
       if (__any_sync(kFull, fail || j < 0)) break;
     }
     // the list the search kernel left behind joins lane 0's (disjoint candidates), then one merge across the lanes

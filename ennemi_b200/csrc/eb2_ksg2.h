@@ -89,6 +89,7 @@ struct LeftEnt {
   int slot;
   int rstart;     // buckets [rstart, NB) are still to be examined on the right (NB: none)
   int lend;       // buckets [0, lend) on the left (0: none)
+  int skip_a;     // slots [skip_a, skip_a + 8) were examined already (the seeds; -16: none are among the remaining buckets)
 };
 
 struct Prob {

@@ -620,6 +620,16 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
     s.launches++;
     return;
   }
+  if (D == 1 && ps.sort_row >= 0 && rows.row[0] == ps.sort_row && !getenv("EB2_NO_KNN1D")) {
+    // one dimension, ascending inside every segment: the k nearest neighbours are among the k predecessors and successors
+    Knn1dArgs g;
+    g.x = ps.P + static_cast<int64_t>(ps.sort_row) * ps.stride; g.tiles = ts.dev; g.ntiles = ts.count; g.k = k;
+    g.eps = eps; g.pairs = pairs;
+    knn1d_kernel<<<ts.count, kThreads, 0, s.c.stream>>>(g);
+    CU(cudaGetLastError());
+    s.launches++;
+    return;
+  }
   KnnArgs a;
   a.P = ps.P; a.stride = ps.stride; a.rows = rows; a.tiles = ts.dev; a.k = k;
   a.sort_row = -1;
@@ -1579,13 +1589,12 @@ double* run_k2(Scratch& s, const k2::Plan& plan, const double* raw, int64_t n, i
   const k2::Shard sh{row_lo, row_hi};
   // the search needs the bucket structure of x only: the y column's grid and the fine cells of both columns (what the
   // marginal counts read) are built on the second stream while layout and search run
+  // (the x buckets get the whole GPU first: they are on the critical path)
   s.used_side = true;
+  CU(k2::colgrid_buckets(dcols, 1, plan, st, &s.launches));
   CU(cudaEventRecord(c.fork, st));
   CU(cudaStreamWaitEvent(c.side, c.fork, 0));
-  CU(k2::colgrid_buckets(dcols, 1, plan, st, &s.launches));
   CU(k2::colgrid_buckets(dcols + 1, 1, plan, c.side, &s.launches));
-  CU(cudaEventRecord(c.fork, st));                  // (re-used: x buckets done)
-  CU(cudaStreamWaitEvent(c.side, c.fork, 0));
   CU(k2::colgrid_cells(dcols, 2, plan, c.side, &s.launches));
   CU(cudaEventRecord(c.join, c.side));
   CU(k2::layout(dcols, dprob, 1, plan, st, &s.launches));

@@ -27,6 +27,8 @@ def test_reference_arm_prints_one_contract_line(monkeypatch):
     assert d["impl"] == "reference" and d["unit"] == "estimates/s" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["metric"].startswith("KSG MI estimates/sec at N=10^6")
+    assert d["config"] == bench.CONFIG            # the GPU arm prints the same dict: the driver compares the two
+    assert "every" not in d["cpu_baseline"]["sample"].split("rows per step")[0] or "ALL" in d["cpu_baseline"]["sample"]
 
 
 def test_other_ranks_of_the_reference_arm_do_nothing(monkeypatch):

@@ -160,6 +160,27 @@ def test_all_pairs_call_matches_single_estimates():
             nat.cache_drop(key)
 
 
+def test_all_pairs_call_outside_the_pipeline():
+    """Sizes / k the pipeline does not take: the same entry point estimates pair by pair on the general path."""
+    rng = np.random.default_rng(9)
+    for n, k in ((1_500, 3), (6_000, 9)):
+        data = rng.normal(size=(n, 4))
+        data[:, 1] += 0.7 * data[:, 0]
+        keys = list(range(9_500, 9_504))
+        for j, key in enumerate(keys):
+            nat.cache_put(key, np.ascontiguousarray(data[:, j]))
+        try:
+            cols = [nat.ColDesc(key, 0, 1, 0.0, 0.0, 0, 0, 1) for key in keys]
+            pairs = np.array([(0, 1), (0, 3), (2, 3)], dtype=np.int32)
+            values, status = nat.ksg_mi_pairs(cols, pairs, n, k)
+            assert not status.any()
+            for t, (i, j) in enumerate(pairs):
+                assert close(values[t], nat.ksg_mi(nat.pack_coords([data[:, i], data[:, j]]), k, flags=BRUTE))
+        finally:
+            for key in keys:
+                nat.cache_drop(key)
+
+
 def test_general_path_takes_over_when_a_bucket_overflows(monkeypatch):
     """Heavily tied data (one value holds most of a column) does not fit the grid's buckets: the call falls back to the
     general path and the answer is still the reference's."""
