@@ -446,6 +446,7 @@ def run_gpu(args):
         ms_e2e, launches_e2e, _, _ = timed_steps(step_e2e, args.steps, args.warmup)
         ebd.enable_row_sharding(True)
         ms_s, _, knn_s, _ = timed_steps(step_sharded, args.steps, args.warmup)
+        sharded_mi, sharded_phases = last["value"], dict(last["phases"])
         # what the exchange alone costs: the same all-reduce of a partial block, nothing else
         blk = np.zeros(nat.P_LEN)
         for _ in range(5):
@@ -455,9 +456,16 @@ def run_gpu(args):
         for _ in range(20):
             ebd._all_reduce_sum(blk)
         reduce_ms = (time.perf_counter() - t0) / 20 * 1e3
+        # the brute-force kernel (every pair evaluated: the FP64-roofline statement of the north star) row-sharded the same way
+        brute_sh = None
+        if not args.no_brute:
+            ms_bs, _, knn_bs, _ = timed_steps(lambda: step_sharded(nat.FLAG_NO_PRUNE), 2, 1)
+            brute_sh = {"ms_per_step": ms_bs / 2, "knn_ms": knn_bs / 2, "mi": last["value"],
+                        "note": "EB2_FLAG_NO_PRUNE, query rows sharded over the ranks: 4e12 FP64 instructions / G per GPU"}
         sharded = {"value": 1e3 / (ms_s / args.steps), "unit": UNIT, "scaling": "strong", "ms_per_step": ms_s / args.steps,
-                   "knn_ms": knn_s / args.steps, "mi": last["value"], "phase_ms": dict(last["phases"]),
-                   "all_reduce_ms": reduce_ms, "speedup_vs_one_gpu_step": None,
+                   "brute_force": brute_sh,
+                   "knn_ms": knn_s / args.steps, "mi": sharded_mi, "phase_ms": sharded_phases,
+                   "all_reduce_ms": reduce_ms,
                    "note": "configs[1]: ONE N=1e6 estimate, the x-buckets (and with them the query rows) sharded over the GPUs; every "
                            "rank builds the whole grid (the point set is replicated), searches and counts its own buckets, and one "
                            "NCCL all-reduce sums the partial blocks, whose digamma sum is an exact integer: the value is bit-identical "
