@@ -542,9 +542,13 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
     if (base_e + __popc(m) <= left_cap) {
       if (want) my_e = (int)(base_e + __popc(m & ((1u << lane) - 1u)));
     } else {
-      // rare (the list is full): finish both directions here, one bucket and one slot at a time
-      if (lane == leader) atomicSub(pr.left_count, (unsigned)__popc(m));
+      // rare (the list is full): finish both directions here, one bucket and one slot at a time.  The reservation is NOT
+      // taken back (a subtraction racing with other warps' reservations would leave holes and lose entries): the counter
+      // only grows, the leftover kernel clamps it at the capacity, and the part of this reservation that still lies
+      // inside the list is marked void.
       if (want) {
+        const unsigned idx = base_e + __popc(m & ((1u << lane) - 1u));
+        if (idx < left_cap) pr.left[idx].slot = -1;
         for (int jj = rstart; jj < NB; ++jj) {
           const int lj = cx.count[jj];
           if (lj == 0) continue;
@@ -595,12 +599,12 @@ __global__ void __launch_bounds__(kThreadsB) knn_kernel2(const Col* cols, const 
 // then scanned by the whole warp, lanes striding over the slots.  Private lists per lane, gated by the k-th distance the
 // search kernel had reached; one merge across the lanes at the end.
 template <int K1T>
-__global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, const Prob* probs, int NB, int k) {
+__global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, const Prob* probs, int NB, int k, unsigned left_cap) {
   const Prob pr = probs[blockIdx.y];
   const Col cx = cols[pr.cx], cy = cols[pr.cy];
   if ((*cx.flag | *cy.flag) != 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned nent = *pr.left_count;
+  const unsigned nent = min(*pr.left_count, left_cap);       // (the counter runs past the capacity when the list was full)
   const double kInf = d_inf();
   const int k1 = k + 1;
   const double* __restrict__ px = pr.px;
@@ -608,6 +612,7 @@ __global__ void __launch_bounds__(kThreadsB) leftover_kernel2(const Col* cols, c
   unsigned long long np = 0;
   for (unsigned e = blockIdx.x * (kThreadsB / 32) + warp; e < nent; e += gridDim.x * (kThreadsB / 32)) {
     const LeftEnt le = pr.left[e];
+    if (le.slot < 0) continue;                               // void: its query was finished by the search kernel
     const double qx = px[le.slot], qy = py[le.slot];
     const double gate = pr.left_best[(long long)e * K1T + (K1T - 1)];      // current k-th distance: upper bound of eps
     const int skip_a = le.skip_a, skip_e = le.skip_a + 8;
@@ -828,6 +833,507 @@ __global__ void final_kernel(const Col* cols, const Prob* probs) {
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+// =====================================================================================================================
+// Three-level grid for spaces of three and more dimensions
+// =====================================================================================================================
+constexpr int kG3Threads = 256;
+constexpr int kG3Heavy = 48;          // cells in a bucket's window above which a query goes to the leftover kernel
+
+// ---- layout: the rows of every bucket of coordinate 0 grouped into C1 x C2 cells over its own ranges of coordinates 1, 2
+__global__ void __launch_bounds__(kG3Threads) layout3_kernel(const Col* col0, const Grid3* gp, long long n, int NB) {
+  __shared__ int s_hist[kMaxCells];
+  __shared__ unsigned short s_cell[kBucketCap];
+  __shared__ double redd[64];
+  __shared__ int red[32];
+  const Grid3 g = *gp;
+  const Col c = *col0;
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) { *g.left_count = 0u; *g.heavy_count = 0u; }
+  if (*c.flag != 0) return;
+  const int len = c.count[b], off = c.boff[b];
+  if (b == NB - 1 && threadIdx.x == 0) { g.cstart[n] = (int)n; g.cstart[n + 1] = (int)n; }
+  if (len == 0) {
+    if (threadIdx.x == 0) { g.g1min[b] = 0.0; g.g1sc[b] = 0.0; g.g2min[b] = 0.0; g.g2sc[b] = 0.0; g.c1n[b] = 1; g.c2n[b] = 1; }
+    return;
+  }
+  if (len > kBucketCap) {                       // (colgrid's fine_cells is not run for these columns: the check lives here)
+    if (threadIdx.x == 0) atomicOr(c.flag, kFlagOverflow);
+    return;
+  }
+  double mn1 = d_inf(), mx1 = -d_inf(), mn2 = d_inf(), mx2 = -d_inf();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int r = c.srow[off + i];
+    const double v1 = g.raw[1][r];
+    mn1 = fmin(mn1, v1); mx1 = fmax(mx1, v1);
+    if (g.G >= 3) { const double v2 = g.raw[2][r]; mn2 = fmin(mn2, v2); mx2 = fmax(mx2, v2); }
+  }
+  block_minmax(mn1, mx1, redd);
+  if (g.G >= 3) block_minmax(mn2, mx2, redd);
+  const int cells = min(len, kMaxCells);
+  int C1 = cells, C2 = 1;
+  if (g.G >= 3) {
+    C1 = max(1, (int)sqrt((double)cells));
+    while (C1 * C1 > cells) --C1;
+    C2 = C1;
+  }
+  const double sc1 = (mx1 > mn1 && mx1 - mn1 < d_inf()) ? (double)C1 / (mx1 - mn1) : 0.0;
+  const double sc2 = (g.G >= 3 && mx2 > mn2 && mx2 - mn2 < d_inf()) ? (double)C2 / (mx2 - mn2) : 0.0;
+  if (threadIdx.x == 0) {
+    g.g1min[b] = mn1; g.g1sc[b] = sc1; g.g2min[b] = g.G >= 3 ? mn2 : 0.0; g.g2sc[b] = sc2; g.c1n[b] = C1; g.c2n[b] = C2;
+  }
+  const int ncell = C1 * C2;
+  for (int f = threadIdx.x; f < ncell; f += blockDim.x) s_hist[f] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int r = c.srow[off + i];
+    int cell = lin_cell(g.raw[1][r], mn1, sc1, C1) * C2;
+    if (g.G >= 3) cell += lin_cell(g.raw[2][r], mn2, sc2, C2);
+    s_cell[i] = (unsigned short)cell;
+    atomicAdd(&s_hist[cell], 1);
+  }
+  __syncthreads();
+  block_excl_scan(s_hist, ncell, red);
+  for (int f = threadIdx.x; f < len; f += blockDim.x) g.cstart[off + f] = f < ncell ? off + s_hist[f] : off + len;
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const int r = c.srow[off + i];
+    const int pos = off + atomicAdd(&s_hist[s_cell[i]], 1);
+    g.pc[0][pos] = c.sval[off + i];
+    for (int d = 1; d < g.D; ++d) g.pc[d][pos] = g.raw[d][r];
+    g.prow[pos] = r;
+    g.pbkt[pos] = (unsigned short)b;
+  }
+}
+
+template <int D>
+struct Pt {
+  double v[D];
+};
+template <int D>
+__device__ __forceinline__ Pt<D> load_pt(const Grid3& g, int s) {
+  Pt<D> p;
+#pragma unroll
+  for (int d = 0; d < D; ++d) p.v[d] = g.pc[d][s];
+  return p;
+}
+// Chebyshev distance if every coordinate difference is below thr, else +inf (the exact test of the search).  The last
+// coordinate goes first and alone: the cells of a window already bound coordinates 0, 1, 2, so in four and more
+// dimensions most rows are turned away by a coordinate the grid knows nothing about, with one load instead of D.
+template <int D>
+__device__ __forceinline__ double cheb_below(const Pt<D>& q, const Grid3& g, int s, double thr) {
+  double m = fabs(q.v[D - 1] - g.pc[D - 1][s]);
+  if (!(m < thr)) return d_inf();
+  bool in = true;
+#pragma unroll
+  for (int d = 0; d < D - 1; ++d) {
+    const double v = fabs(q.v[d] - g.pc[d][s]);
+    in = in && v < thr;
+    m = v > m ? v : m;
+  }
+  return in ? m : d_inf();
+}
+
+// cell windows of bucket j for a box of half-width t around q (coordinates 1 and 2), widened by 2^-50 relative
+struct Win3 {
+  int f1lo, f1hi, f2lo, f2hi, C2, off;
+};
+__device__ __forceinline__ Win3 window3(const Grid3& g, const Col& c, int j, double q1, double q2, double t) {
+  Win3 w;
+  w.off = c.boff[j];
+  const int C1 = g.c1n[j];
+  w.C2 = g.c2n[j];
+  w.f1lo = 0; w.f1hi = C1 - 1; w.f2lo = 0; w.f2hi = w.C2 - 1;
+  if (t < d_inf()) {
+    const double m1 = g.g1min[j], s1 = g.g1sc[j];
+    w.f1lo = lin_cell((q1 - t) - (fabs(q1) + t) * kSlack, m1, s1, C1);
+    w.f1hi = lin_cell((q1 + t) + (fabs(q1) + t) * kSlack, m1, s1, C1);
+    if (w.C2 > 1) {
+      const double m2 = g.g2min[j], s2 = g.g2sc[j];
+      w.f2lo = lin_cell((q2 - t) - (fabs(q2) + t) * kSlack, m2, s2, w.C2);
+      w.f2hi = lin_cell((q2 + t) + (fabs(q2) + t) * kSlack, m2, s2, w.C2);
+    }
+  }
+  return w;
+}
+
+template <int K1T>
+__device__ __forceinline__ double kth_of(const double (&best)[K1T], int k) {
+  double r = best[0];
+#pragma unroll
+  for (int t = 1; t < K1T; ++t) r = (t <= k) ? best[t] : r;
+  return r;
+}
+// the next double above v >= 0 (a gate that lets distances EQUAL to a known bound through the strict test)
+__device__ __forceinline__ double next_up(double v) {
+  return v < d_inf() ? __longlong_as_double(__double_as_longlong(v) + 1) : v;
+}
+
+constexpr int kG3Pre = 2;             // bounding pass: cells either side of the query's own, per grid coordinate
+
+// The cells of coordinates 1, 2 say nothing about the remaining coordinates of a row: a list seeded from the rows next
+// to the query in slot order starts with a k-th distance of the order of the whole range of those coordinates, and every
+// window cut at it is most of its bucket.  So the search runs in two passes.  Bounding pass: the rows of the
+// (2 kG3Pre + 1)^2 cells around the query's own cell in its own bucket (a few dozen rows, all close in coordinates
+// 0, 1, 2) are real points of the set, the query among them: their (k + 1)-th smallest distance bounds the true one
+// from above.  Exact pass: a fresh list, gated by the next double above that bound, over the windows of every bucket
+// the gate reaches, nearest first, the gate tightening to the running k-th distance.  Every row within the true k-th
+// distance passes the gate and lies in the windows (monotone cell maps, thresholds widened by 2^-50), so the list ends
+// as the exhaustive search's: bit-exact.  Windows of more than kG3Heavy cells, or more than `near` buckets on a side,
+// are left to leftover3_kernel from that bucket on.
+template <int D, int K1T>
+__global__ void __launch_bounds__(kG3Threads) knn3_kernel(const Col* col0, const Grid3* gp, long long n, int NB, int k, int near,
+                                                           int heavy_cells) {
+  const Grid3 g = *gp;
+  const Col c = *col0;
+  if (*c.flag != 0) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned nblk = gridDim.x;
+  const unsigned blk = (blockIdx.x & 1u) ? nblk - 1u - (blockIdx.x >> 1) : (blockIdx.x >> 1);     // both ends of coordinate 0 first
+  const long long s64 = (long long)blk * kG3Threads + threadIdx.x;
+  const int slot = (int)min(s64, n - 1);
+  const bool valid = s64 < n;
+  const int b = g.pbkt[slot];
+  const int off = c.boff[b];
+  const Pt<D> q = load_pt<D>(g, slot);
+  const double kInf = d_inf();
+  unsigned long long np = 0;
+  double best[K1T];
+#pragma unroll
+  for (int t = 0; t < K1T; ++t) best[t] = kInf;
+  double thr = kInf;
+  if (valid) {                                        // ---- bounding pass
+    const int C1 = g.c1n[b], C2 = g.c2n[b];
+    const int c1q = lin_cell(q.v[1], g.g1min[b], g.g1sc[b], C1);
+    const int c2q = C2 > 1 ? lin_cell(q.v[2], g.g2min[b], g.g2sc[b], C2) : 0;
+    // the neighbourhood grows until it holds a few times k + 1 rows (sparse corners of a bucket's cell grid) or the bucket
+    const int need = 4 * (k + 1);
+    int r = kG3Pre, f1lo, f1hi, f2lo, f2hi;
+    for (;;) {
+      const int r1 = C2 > 1 ? r : 2 * r * (r + 1);                          // (one cell coordinate: as many cells in a row)
+      f1lo = max(c1q - r1, 0); f1hi = min(c1q + r1, C1 - 1);
+      f2lo = max(c2q - r, 0); f2hi = min(c2q + r, C2 - 1);
+      if (f1lo == 0 && f1hi == C1 - 1 && f2lo == 0 && f2hi == C2 - 1) break;
+      int cnt = 0;
+      for (int c1 = f1lo; c1 <= f1hi; ++c1) cnt += g.cstart[off + c1 * C2 + f2hi + 1] - g.cstart[off + c1 * C2 + f2lo];
+      if (cnt >= need) break;
+      r *= 2;
+    }
+    for (int c1 = f1lo; c1 <= f1hi; ++c1) {
+      const int a = g.cstart[off + c1 * C2 + f2lo], e = g.cstart[off + c1 * C2 + f2hi + 1];
+      for (int s = a; s < e; ++s) {
+        const double m = cheb_below<D>(q, g, s, thr);
+        if (m < thr) {
+          topk_insert<K1T>(best, m);
+          thr = kth_of<K1T>(best, k);
+        }
+      }
+      if (e > a) np += (unsigned long long)(e - a);
+    }
+  }
+  const double gate = next_up(thr);
+#pragma unroll
+  for (int t = 0; t < K1T; ++t) best[t] = kInf;
+  thr = gate;
+  // ---- exact pass.  Every run of bucket j's window; false: the window is too large for one thread (nothing was examined)
+  auto visit = [&](int j) -> bool {
+    const Win3 w = window3(g, c, j, q.v[1], q.v[2], thr);
+    if ((w.f1hi - w.f1lo + 1) * (w.f2hi - w.f2lo + 1) > heavy_cells) return false;
+    for (int c1 = w.f1lo; c1 <= w.f1hi; ++c1) {
+      const int a = g.cstart[w.off + c1 * w.C2 + w.f2lo], e = g.cstart[w.off + c1 * w.C2 + w.f2hi + 1];
+      for (int s = a; s < e; ++s) {
+        const double m = cheb_below<D>(q, g, s, thr);
+        if (m < thr) {
+          topk_insert<K1T>(best, m);
+          thr = fmin(gate, kth_of<K1T>(best, k));
+        }
+      }
+      if (e > a) np += (unsigned long long)(e - a);
+    }
+    return true;
+  };
+  int rstart = NB, lend = 0;
+  bool heavy = false;
+  if (valid && !visit(b)) { heavy = true; rstart = b; lend = b; }
+  {
+    bool more = valid && !heavy;
+    int j = b + 1;
+    for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
+      if (more) {
+        while (j < NB && c.count[j] == 0) ++j;
+        if (j >= NB || (c.vlo[j] - q.v[0]) >= thr) more = false;
+        else if (!visit(j)) { rstart = j; more = false; }
+        else ++j;
+      }
+    }
+    if (more) {
+      while (j < NB && c.count[j] == 0) ++j;
+      if (j < NB && !((c.vlo[j] - q.v[0]) >= thr)) rstart = j;
+    }
+  }
+  {
+    bool more = valid && !heavy;
+    int j = b - 1;
+    for (int t = 0; t < near && __any_sync(kFull, more); ++t) {
+      if (more) {
+        while (j >= 0 && c.count[j] == 0) --j;
+        if (j < 0 || (q.v[0] - c.vhi[j]) >= thr) more = false;
+        else if (!visit(j)) { lend = j + 1; more = false; }
+        else --j;
+      }
+    }
+    if (more) {
+      while (j >= 0 && c.count[j] == 0) --j;
+      if (j >= 0 && !((q.v[0] - c.vhi[j]) >= thr)) lend = j + 1;
+    }
+  }
+  const bool want = valid && (rstart < NB || lend > 0);
+  const unsigned m = __ballot_sync(kFull, want);
+  int my_e = -1;
+  if (m != 0) {
+    const int leader = __ffs(m) - 1;
+    unsigned base_e = 0;
+    if (lane == leader) base_e = atomicAdd(g.left_count, (unsigned)__popc(m));
+    base_e = __shfl_sync(kFull, base_e, leader);
+    if (want) my_e = (int)(base_e + __popc(m & ((1u << lane) - 1u)));       // (the list holds one entry per row: never full)
+  }
+  if (valid) {
+    if (my_e >= 0) {
+      LeftEnt le;
+      le.slot = slot; le.rstart = rstart; le.lend = lend; le.skip_a = heavy ? 1 : 0;
+      g.left[my_e] = le;
+      g.eps[slot] = thr;                                 // the gate the leftover kernel starts from
+#pragma unroll
+      for (int t = 0; t < K1T; ++t) g.left_best[(long long)my_e * K1T + t] = best[t];
+    } else {
+      const double r = kth_of<K1T>(best, k);
+      g.eps[slot] = r;
+      g.eps_row[g.prow[slot]] = r;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_down_sync(kFull, np, o);
+  if (lane == 0 && np && g.pairs) atomicAdd(g.pairs, np);
+}
+
+// One warp per deferred query: the lanes take the remaining buckets round-robin, each walking the runs of its bucket's
+// window on its own; private lists per lane, gated by min(gate, the lane's own k-th distance), merged at the end with the
+// list the query's thread left.  A query without a bound (fewer than k + 1 rows in its own bucket) first gets one from
+// whole buckets, its own outwards.
+template <int D, int K1T>
+__global__ void __launch_bounds__(kG3Threads) leftover3_kernel(const Col* col0, const Grid3* gp, int NB, int k) {
+  const Grid3 g = *gp;
+  const Col c = *col0;
+  if (*c.flag != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nent = *g.left_count;
+  const double kInf = d_inf();
+  const int k1 = k + 1;
+  unsigned long long np = 0;
+  for (unsigned e = blockIdx.x * (kG3Threads / 32) + warp; e < nent; e += gridDim.x * (kG3Threads / 32)) {
+    const LeftEnt le = g.left[e];
+    const Pt<D> q = load_pt<D>(g, le.slot);
+    double gate = g.eps[le.slot];
+    double best[K1T];
+    if (!(gate < kInf)) {
+      // no bound yet (the query's own bucket holds fewer than k + 1 rows): whole buckets, its own first, then outwards,
+      // until k + 1 rows have been seen; their (k + 1)-th smallest distance is the bound
+      const int b = g.pbkt[le.slot];
+#pragma unroll
+      for (int u = 0; u < K1T; ++u) best[u] = kInf;
+      double bound = kInf;
+      for (int t = 0; !(bound < kInf) && t < NB; ++t) {
+        for (int side = 0; side < (t == 0 ? 1 : 2); ++side) {
+          const int j = side == 0 ? b + t : b - t;
+          if (j < 0 || j >= NB) continue;
+          const int jo = c.boff[j], jl = c.count[j];
+          for (int s = jo + lane; s < jo + jl; s += 32) {
+            const double m = cheb_below<D>(q, g, s, kInf);
+            if (m < best[K1T - 1]) topk_insert<K1T>(best, m);
+          }
+        }
+        bound = __shfl_sync(kFull, warp_merge_lists<K1T>(best, k1), k);
+      }
+      gate = next_up(bound);
+    }
+#pragma unroll
+    for (int t = 0; t < K1T; ++t) best[t] = kInf;
+    double thr = gate;
+    // the lanes take the remaining buckets round-robin, each walking the runs of its bucket's window on its own
+    auto bucket = [&](int j) {
+      const Win3 w = window3(g, c, j, q.v[1], q.v[2], thr);
+      for (int c1 = w.f1lo; c1 <= w.f1hi; ++c1) {
+        const int a = g.cstart[w.off + c1 * w.C2 + w.f2lo], en = g.cstart[w.off + c1 * w.C2 + w.f2hi + 1];
+        for (int s = a; s < en; ++s) {
+          const double m = cheb_below<D>(q, g, s, thr);
+          if (m < thr) {
+            topk_insert<K1T>(best, m);
+            thr = fmin(best[K1T - 1], gate);
+          }
+        }
+        if (en > a) np += (unsigned long long)(en - a);
+      }
+    };
+    for (int j = le.rstart + lane; j < NB; j += 32) {
+      if (c.count[j] == 0) continue;
+      if ((c.vlo[j] - q.v[0]) >= thr) break;                 // (vlo ascends with j: every later bucket of this lane fails too)
+      bucket(j);
+    }
+    for (int j = le.lend - 1 - lane; j >= 0; j -= 32) {
+      if (c.count[j] == 0) continue;
+      if ((q.v[0] - c.vhi[j]) >= thr) break;
+      bucket(j);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < K1T; ++t) {
+        const double v = g.left_best[(long long)e * K1T + t];
+        if (v < best[K1T - 1]) topk_insert<K1T>(best, v);
+      }
+    }
+    const double fin = warp_merge_lists<K1T>(best, k1);
+    if (lane == k) { g.eps[le.slot] = fin; g.eps_row[g.prow[le.slot]] = fin; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_down_sync(kFull, np, o);
+  if (lane == 0 && np && g.pairs) atomicAdd(g.pairs, np);
+}
+
+
+// Frenzel-Pompe counts (:152-154): coordinates [0, C) are the condition z, C is x, C + 1 is y; radius r = eps - 1e-12,
+// inclusive.  One thread per query walks the runs of the windows of the buckets its radius reaches; queries with a wide
+// radius (sparse regions: windows of many cells, or many buckets) are left to count3_heavy_kernel, a warp each.
+constexpr int kG3CountBuckets = 64;
+template <int C>
+__global__ void __launch_bounds__(kG3Threads) count3_kernel(const Col* col0, const Grid3* gp, long long n, int NB) {
+  constexpr int D = C + 2;
+  const Grid3 g = *gp;
+  const Col c = *col0;
+  if (*c.flag != 0) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned nblk = gridDim.x;
+  const unsigned blk = (blockIdx.x & 1u) ? nblk - 1u - (blockIdx.x >> 1) : (blockIdx.x >> 1);
+  const long long s64 = (long long)blk * kG3Threads + threadIdx.x;
+  const bool valid = s64 < n;
+  const int slot = (int)min(s64, n - 1);
+  const Pt<D> q = load_pt<D>(g, slot);
+  const double r = g.eps[slot] - 1e-12;                      // _entropy_estimators.py:109
+  int nz = 0, nxz = 0, nyz = 0;
+  unsigned long long np = 0;
+  bool defer = false;
+  if (valid && r >= 0.0) {
+    const int b = g.pbkt[slot];
+    auto bucket = [&](int j) -> bool {
+      const Win3 w = window3(g, c, j, q.v[1], q.v[2], r);      // (the window of a box of half-width r, widened: a superset)
+      if ((w.f1hi - w.f1lo + 1) * (w.f2hi - w.f2lo + 1) > kG3Heavy) return false;
+      for (int c1 = w.f1lo; c1 <= w.f1hi; ++c1) {
+        const int a = g.cstart[w.off + c1 * w.C2 + w.f2lo], e = g.cstart[w.off + c1 * w.C2 + w.f2hi + 1];
+        for (int s = a; s < e; ++s) {
+          bool in = true;
+#pragma unroll
+          for (int d = 0; d < C; ++d) in = in && fabs(q.v[d] - g.pc[d][s]) <= r;
+          if (in) {
+            ++nz;
+            nxz += (int)(fabs(q.v[C] - g.pc[C][s]) <= r);
+            nyz += (int)(fabs(q.v[C + 1] - g.pc[C + 1][s]) <= r);
+          }
+        }
+        if (e > a) np += (unsigned long long)(e - a);
+      }
+      return true;
+    };
+    defer = !bucket(b);
+    // a bucket can hold a row within r only while the gap in coordinate 0 does not exceed r (rounded subtraction is
+    // monotone; the values of bucket j lie in (vlo, vhi])
+    int visited = 0;
+    for (int j = b + 1; j < NB && !defer; ++j) {
+      if (c.count[j] == 0) continue;
+      if ((c.vlo[j] - q.v[0]) > r) break;
+      if (++visited > kG3CountBuckets || !bucket(j)) defer = true;
+    }
+    for (int j = b - 1; j >= 0 && !defer; --j) {
+      if (c.count[j] == 0) continue;
+      if ((q.v[0] - c.vhi[j]) > r) break;
+      if (++visited > kG3CountBuckets || !bucket(j)) defer = true;
+    }
+  }
+  const unsigned m = __ballot_sync(kFull, defer);
+  if (m != 0) {
+    const int leader = __ffs(m) - 1;
+    unsigned base_e = 0;
+    if (lane == leader) base_e = atomicAdd(g.heavy_count, (unsigned)__popc(m));
+    base_e = __shfl_sync(kFull, base_e, leader);
+    if (defer) g.heavy[base_e + __popc(m & ((1u << lane) - 1u))] = slot;
+  }
+  if (valid && !defer) {
+    const int row = g.prow[slot];
+    g.cnt_row[0][row] = nz;
+    g.cnt_row[1][row] = nxz;
+    g.cnt_row[2][row] = nyz;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_down_sync(kFull, np, o);
+  if (lane == 0 && np && g.pairs) atomicAdd(g.pairs, np);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kG3Threads) count3_heavy_kernel(const Col* col0, const Grid3* gp, int NB) {
+  constexpr int D = C + 2;
+  const Grid3 g = *gp;
+  const Col c = *col0;
+  if (*c.flag != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nent = *g.heavy_count;
+  unsigned long long np = 0;
+  for (unsigned e = blockIdx.x * (kG3Threads / 32) + warp; e < nent; e += gridDim.x * (kG3Threads / 32)) {
+    const int slot = g.heavy[e];
+    const Pt<D> q = load_pt<D>(g, slot);
+    const double r = g.eps[slot] - 1e-12;
+    int nz = 0, nxz = 0, nyz = 0;
+    auto bucket = [&](int j) {
+      const Win3 w = window3(g, c, j, q.v[1], q.v[2], r);
+      for (int c1 = w.f1lo; c1 <= w.f1hi; ++c1) {
+        const int a = g.cstart[w.off + c1 * w.C2 + w.f2lo], en = g.cstart[w.off + c1 * w.C2 + w.f2hi + 1];
+        for (int s = a + lane; s < en; s += 32) {
+          bool in = true;
+#pragma unroll
+          for (int d = 0; d < C; ++d) in = in && fabs(q.v[d] - g.pc[d][s]) <= r;
+          if (in) {
+            ++nz;
+            nxz += (int)(fabs(q.v[C] - g.pc[C][s]) <= r);
+            nyz += (int)(fabs(q.v[C + 1] - g.pc[C + 1][s]) <= r);
+          }
+        }
+        if (lane == 0 && en > a) np += (unsigned long long)(en - a);
+      }
+    };
+    const int b = g.pbkt[slot];
+    bucket(b);
+    for (int j = b + 1; j < NB; ++j) {
+      if (c.count[j] == 0) continue;
+      if ((c.vlo[j] - q.v[0]) > r) break;
+      bucket(j);
+    }
+    for (int j = b - 1; j >= 0; --j) {
+      if (c.count[j] == 0) continue;
+      if ((q.v[0] - c.vhi[j]) > r) break;
+      bucket(j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nz += __shfl_xor_sync(kFull, nz, o);
+      nxz += __shfl_xor_sync(kFull, nxz, o);
+      nyz += __shfl_xor_sync(kFull, nyz, o);
+    }
+    if (lane == 0) {
+      const int row = g.prow[slot];
+      g.cnt_row[0][row] = nz;
+      g.cnt_row[1][row] = nxz;
+      g.cnt_row[2][row] = nyz;
+    }
+  }
+  if (lane == 0 && np && g.pairs) atomicAdd(g.pairs, np);
+}
+
 }  // namespace
 
 Plan make_plan(int64_t n, bool* ok) {
@@ -899,7 +1405,11 @@ Col carve_col(char* base, int64_t n, const double* vals) {
 }
 
 // entries the deferral list of a problem can hold (a full list only means that the search kernel keeps going itself)
-static size_t left_cap(const Plan& p) { return static_cast<size_t>(p.n / 4 + 1024); }
+static size_t left_cap(const Plan& p) {
+  size_t cap = static_cast<size_t>(p.n / 4 + 1024);
+  if (const char* e = getenv("EB2_K2_LEFTCAP")) cap = std::min(cap, static_cast<size_t>(std::max(1LL, atoll(e))));   // test knob: a full list
+  return cap;
+}
 
 size_t prob_bytes(const Plan& p, int k1t) {
   size_t b = 0;
@@ -976,10 +1486,10 @@ cudaError_t knn(const Col* cols, const Prob* probs, int nprob, const Plan& p, in
   const unsigned cap = static_cast<unsigned>(left_cap(p));
   if (k + 1 <= 4) {
     knn_kernel2<4><<<dim3(grid, nprob), kThreadsB, 0, s>>>(cols, probs, p.n, p.NB, k, near, cap, sh);
-    leftover_kernel2<4><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k);
+    leftover_kernel2<4><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k, cap);
   } else if (k + 1 <= 8) {
     knn_kernel2<8><<<dim3(grid, nprob), kThreadsB, 0, s>>>(cols, probs, p.n, p.NB, k, near, cap, sh);
-    leftover_kernel2<8><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k);
+    leftover_kernel2<8><<<dim3(lgrid, nprob), kThreadsB, 0, s>>>(cols, probs, p.NB, k, cap);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -999,6 +1509,132 @@ cudaError_t finalize(const Col* cols, const Prob* probs, int nprob, const Plan& 
   (void)p;
   final_kernel<<<nprob, 1, 0, s>>>(cols, probs);
   if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+
+// ---- three-level grid: host side ---------------------------------------------------------------------------------------
+Plan make_plan3(int64_t n, int D, bool* ok) {
+  (void)D;
+  Plan p;
+  p.n = n;
+  // buckets of ~2,048 rows (C1 x C2 = 45 x 45 cells; a quarter of what a bucket may hold: the quantile estimates from 8
+  // samples per bucket scatter by +-35 %): in three and more dimensions a k-th neighbour distance spans several buckets anyway
+  int64_t rows = 2048;
+  if (const char* e = getenv("EB2_G3_ROWS")) rows = atoll(e);           // tuning knob
+  if (rows < 256) rows = 256;
+  if (rows > kBucketCap / 2) rows = kBucketCap / 2;
+  int64_t Bc = (n + rows - 1) / rows;
+  if (Bc < 1) Bc = 1;
+  bool fits = n >= 2 && n < (int64_t(1) << 30);
+  if (Bc > kMaxCoarse) { Bc = kMaxCoarse; if (n > int64_t(kMaxCoarse) * (kBucketCap / 2)) fits = false; }
+  p.Bc = static_cast<int>(Bc);
+  p.NB = p.Bc * kSub;
+  int64_t over = n / Bc;                                          // (as many samples per bucket as the ranking holds: the fuller
+  if (over > 32) over = 32;                                       //  buckets of this grid need tighter quantiles)
+  if (over < 1) over = 1;
+  while (over > 1 && over * Bc > 4096) --over;
+  p.over = static_cast<int>(over);
+  if (ok) *ok = fits;
+  return p;
+}
+
+size_t grid3_bytes(const Plan& p, int D, int k1t) {
+  size_t b = 0;
+  b += align256(sizeof(double) * p.n) * (D + 2);              // pc, eps, eps_row
+  b += align256(sizeof(int) * p.n) * 5;                       // prow, cnt_row x3, heavy
+  b += align256(sizeof(unsigned short) * p.n);                // pbkt
+  b += align256(sizeof(int) * (p.n + 2));                     // cstart
+  b += align256(sizeof(double) * kMaxBuckets) * 4;            // cell maps
+  b += align256(sizeof(int) * kMaxBuckets) * 2;               // c1n, c2n
+  b += align256(sizeof(LeftEnt) * p.n);                       // left
+  b += align256(sizeof(double) * p.n * k1t);                  // left_best
+  b += 256 * 3;                                               // left_count, pairs (caller's), spare
+  return b;
+}
+
+Grid3 carve_grid3(char* base, const Plan& p, int D, int G, int k1t) {
+  Grid3 g;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { char* ptr = base + o; o += align256(bytes); return ptr; };
+  g.D = D; g.G = G;
+  for (int d = 0; d < kG3MaxD; ++d) { g.raw[d] = nullptr; g.pc[d] = nullptr; }
+  for (int d = 0; d < D; ++d) g.pc[d] = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  g.eps = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  g.eps_row = reinterpret_cast<double*>(take(sizeof(double) * p.n));
+  g.prow = reinterpret_cast<int*>(take(sizeof(int) * p.n));
+  for (int i = 0; i < 3; ++i) g.cnt_row[i] = reinterpret_cast<int*>(take(sizeof(int) * p.n));
+  g.pbkt = reinterpret_cast<unsigned short*>(take(sizeof(unsigned short) * p.n));
+  g.cstart = reinterpret_cast<int*>(take(sizeof(int) * (p.n + 2)));
+  g.g1min = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  g.g1sc = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  g.g2min = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  g.g2sc = reinterpret_cast<double*>(take(sizeof(double) * kMaxBuckets));
+  g.c1n = reinterpret_cast<int*>(take(sizeof(int) * kMaxBuckets));
+  g.c2n = reinterpret_cast<int*>(take(sizeof(int) * kMaxBuckets));
+  g.left = reinterpret_cast<LeftEnt*>(take(sizeof(LeftEnt) * p.n));
+  g.left_best = reinterpret_cast<double*>(take(sizeof(double) * p.n * k1t));
+  g.left_count = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int)));
+  g.heavy_count = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int)));
+  g.heavy = reinterpret_cast<int*>(take(sizeof(int) * p.n));
+  g.pairs = nullptr;
+  g.flag = nullptr;
+  return g;
+}
+
+cudaError_t layout3(const Col* col0, const Grid3* g, const Plan& p, cudaStream_t s, int* launches) {
+  layout3_kernel<<<p.NB, kG3Threads, 0, s>>>(col0, g, p.n, p.NB);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t knn3_d(const Col* col0, const Grid3* g, const Plan& p, int k, int near, int sm_count, cudaStream_t s) {
+  const int grid = static_cast<int>((p.n + kG3Threads - 1) / kG3Threads);
+  int heavy = 256;       // cells of one bucket's window a single thread still walks (the lanes of a warp are neighbours:
+                         // their windows are alike)
+  if (const char* e = getenv("EB2_G3_HEAVY")) heavy = atoi(e);        // tuning knob
+  if (k + 1 <= 4) {
+    knn3_kernel<D, 4><<<grid, kG3Threads, 0, s>>>(col0, g, p.n, p.NB, k, near, heavy);
+    leftover3_kernel<D, 4><<<sm_count * 8, kG3Threads, 0, s>>>(col0, g, p.NB, k);
+  } else {
+    knn3_kernel<D, 8><<<grid, kG3Threads, 0, s>>>(col0, g, p.n, p.NB, k, near, heavy);
+    leftover3_kernel<D, 8><<<sm_count * 8, kG3Threads, 0, s>>>(col0, g, p.NB, k);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t knn3(const Col* col0, const Grid3* g, const Grid3& h, const Plan& p, int k, int sm_count, cudaStream_t s, int* launches) {
+  if (k + 1 > 8) return cudaErrorInvalidValue;
+  int near = 48;         // (buckets are narrower than a k-th distance in 3+ dimensions: a query visits a few dozen)
+  if (const char* e = getenv("EB2_G3_NEAR")) near = atoi(e);          // tuning knob
+  if (launches) *launches += 2;
+  switch (h.D) {
+    case 3: return knn3_d<3>(col0, g, p, k, near, sm_count, s);
+    case 4: return knn3_d<4>(col0, g, p, k, near, sm_count, s);
+    case 5: return knn3_d<5>(col0, g, p, k, near, sm_count, s);
+    case 6: return knn3_d<6>(col0, g, p, k, near, sm_count, s);
+    case 7: return knn3_d<7>(col0, g, p, k, near, sm_count, s);
+    case 8: return knn3_d<8>(col0, g, p, k, near, sm_count, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t count3(const Col* col0, const Grid3* g, const Grid3& h, const Plan& p, int C, cudaStream_t s, int* launches) {
+  (void)h;
+  const int grid = static_cast<int>((p.n + kG3Threads - 1) / kG3Threads);
+  const int hgrid = 148 * 8;
+  switch (C) {
+#define EB2_G3_COUNT(CC)                                                                  \
+    case CC:                                                                              \
+      count3_kernel<CC><<<grid, kG3Threads, 0, s>>>(col0, g, p.n, p.NB);                  \
+      count3_heavy_kernel<CC><<<hgrid, kG3Threads, 0, s>>>(col0, g, p.NB);                \
+      break;
+    EB2_G3_COUNT(2) EB2_G3_COUNT(3) EB2_G3_COUNT(4) EB2_G3_COUNT(5) EB2_G3_COUNT(6)
+#undef EB2_G3_COUNT
+    default: return cudaErrorInvalidValue;
+  }
+  if (launches) *launches += 2;
   return cudaGetLastError();
 }
 

@@ -136,5 +136,41 @@ cudaError_t count_psi(const Col* cols, const Prob* probs, int nprob, const Plan&
 // fills probs[p].out from the accumulators and ORs the column flags into out[5]
 cudaError_t finalize(const Col* cols, const Prob* probs, int nprob, const Plan& p, cudaStream_t s, int* launches);
 
+
+// ---- three-level grid for spaces of three and more dimensions (k-NN entropy :21-42, Frenzel-Pompe :116-156) ----------
+// Same construction one level deeper: buckets of coordinate 0 (a Col built by colgrid_buckets), and inside every bucket
+// cells over the bucket's own ranges of coordinates 1 and 2 (C1 x C2 <= 4,096 cells, about one row each), built by
+// counting.  All D coordinates travel with the rows; a window in coordinates 0..2 is a few runs of consecutive slots.
+constexpr int kG3MaxD = 8;
+
+struct Grid3 {
+  int D;                      // coordinates of the space (3 .. kG3MaxD); 0, 1, 2 are the grid coordinates
+  int G;                      // grid levels in use: 2 (cells on coordinate 1 only) or 3
+  const double* raw[kG3MaxD]; // coordinate rows, caller's row order (raw[0] = the bucket column's vals)
+  double* pc[kG3MaxD];        // [n] coordinates in slot order
+  int* prow;                  // [n] slot -> row
+  unsigned short* pbkt;       // [n] slot -> bucket
+  int* cstart;                // [n + 2] first slot of cell boff[b] + c1 * C2 + c2
+  double* g1min; double* g1sc; double* g2min; double* g2sc;   // [kMaxBuckets] cell maps per bucket
+  int* c1n; int* c2n;         // [kMaxBuckets] cells per bucket along coordinates 1 and 2
+  double* eps_row;            // [n] k-th distance per ROW
+  double* eps;                // [n] per slot
+  LeftEnt* left; double* left_best; unsigned int* left_count;
+  int* heavy; unsigned int* heavy_count;   // [n] slots whose counts are taken by a warp (wide radius), their number
+  int* cnt_row[3];            // per row: n_z, n_xz, n_yz (Frenzel-Pompe), or NULL
+  unsigned long long* pairs;  // work counter
+  int* flag;                  // ORed with the bucket column's flag by the kernels' callers
+};
+size_t grid3_bytes(const Plan& p, int D, int k1t);
+Grid3 carve_grid3(char* base, const Plan& p, int D, int G, int k1t);
+// plan for a D-dimensional space (bucket size differs from the bivariate one)
+Plan make_plan3(int64_t n, int D, bool* ok);
+
+cudaError_t layout3(const Col* col0, const Grid3* g, const Plan& p, cudaStream_t s, int* launches);
+cudaError_t knn3(const Col* col0, const Grid3* g, const Grid3& host_copy, const Plan& p, int k, int sm_count, cudaStream_t s,
+                 int* launches);
+// Frenzel-Pompe counts: coordinates [0, C) are the condition, C and C + 1 are x and y
+cudaError_t count3(const Col* col0, const Grid3* g, const Grid3& host_copy, const Plan& p, int C, cudaStream_t s, int* launches);
+
 }  // namespace k2
 }  // namespace eb2

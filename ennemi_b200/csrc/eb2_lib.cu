@@ -1612,6 +1612,74 @@ double* run_k2(Scratch& s, const k2::Plan& plan, const double* raw, int64_t n, i
   return s.result;
 }
 
+// ---- three-level grid (eb2_ksg2.h) for one estimate in a space of three and more dimensions ----------------------------
+__global__ void g3_setup_kernel(const k2::Col c, const k2::Grid3 g, k2::Col* dc, k2::Grid3* dg) {
+  *dc = c;
+  *dg = g;
+  *c.flag = 0;
+}
+__global__ void widen_kernel(const int* src, long long* dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// Smallest input the three-level grid takes in a space of `dims` dimensions.  Measured on a B200 (tools/g3_time.py,
+// k-NN entropy, grid vs general path): N = 5*10^5: 3-D 1.7 vs 2.3 ms, 4-D 7.8 vs 19.7 ms, 5-D 45 vs 29 ms; 4-D at
+// N = 2*10^6: 25 vs 67 ms, at N = 10^5: 0.88 vs 0.67 ms.  The grid orders three coordinates; from the fifth dimension on
+// too much of a window is rows that only differ in the coordinates it does not order.
+int64_t g3_min_rows(int dims) {
+  if (const char* e = getenv("EB2_G3_MIN")) return atoll(e);     // tuning / test knob (every dimension)
+  return dims <= 4 ? 200000 : INT64_MAX;
+}
+
+// tiles over the rows [0, n) in the caller's order (the grid kernels leave their per-query results by ROW, so that the
+// digamma / log reduction runs in a fixed order whatever order the grid put the rows in)
+TileSet row_tiles(Scratch& s, int64_t n) {
+  PointSet ps;
+  ps.qpt = kMaxQpt; ps.d = 1; ps.n = n; ps.stride = n; ps.sort_row = -1;
+  ps.seg_slot = {0};
+  ps.seg_len = {static_cast<int>(n)};
+  return make_tiles(s, ps, 0, n, true, 0, 0);
+}
+
+struct G3Run {
+  k2::Grid3 host;        // device pointers of the grid
+  TileSet rows;
+};
+
+// rows_src[d]: coordinate d of the space, d < D, on the device; coordinates 0 .. G-1 carry the grid
+G3Run run_g3(Scratch& s, const k2::Plan& plan, const double* const* rows_src, int D, int G, int64_t n, int k, int count_c,
+             const CallInit& ci) {
+  Ctx& c = s.c;
+  cudaStream_t st = c.stream;
+  c.last_pipeline = 2;
+  const int k1t = (k + 1 <= 4) ? 4 : 8;
+  k2::Col hc = k2::carve_col(s.dev<char>(k2::col_bytes(n)), n, rows_src[0]);
+  k2::Grid3 hg = k2::carve_grid3(s.dev<char>(k2::grid3_bytes(plan, D, k1t)), plan, D, G, k1t);
+  for (int d = 0; d < D; ++d) hg.raw[d] = rows_src[d];
+  hg.pairs = ci.pairs;
+  // (a call that ends in a bucket overflow still runs its reduction kernels: they must not see uninitialised counts)
+  CU(cudaMemsetAsync(hg.eps_row, 0, sizeof(double) * n, st));
+  if (count_c > 0)
+    for (int i = 0; i < 3; ++i) CU(cudaMemsetAsync(hg.cnt_row[i], 0, sizeof(int) * n, st));
+  k2::Col* dcol = s.dev<k2::Col>(1);
+  k2::Grid3* dg = s.dev<k2::Grid3>(1);
+  g3_setup_kernel<<<1, 1, 0, st>>>(hc, hg, dcol, dg);
+  s.launches++;
+  CU(k2::colgrid_buckets(dcol, 1, plan, st, &s.launches));
+  CU(k2::layout3(dcol, dg, plan, st, &s.launches));
+  mark(s, 1);
+  CU(k2::knn3(dcol, dg, hg, plan, k, c.sm_count, st, &s.launches));
+  mark(s, 2);
+  if (count_c > 0) CU(k2::count3(dcol, dg, hg, plan, count_c, st, &s.launches));
+  or_flags_kernel<<<1, 1, 0, st>>>(ci.nonfinite, hc.flag, nullptr);          // a bucket overflow sends the call to the general path
+  s.launches++;
+  G3Run r;
+  r.host = hg;
+  r.rows = row_tiles(s, n);
+  return r;
+}
+
 // ---- a1: KSG ------------------------------------------------------------------------------------
 static int ksg_rows_once(int dev, const Input& in, int64_t n, int k, int64_t row_lo, int64_t row_hi,
                          double* partial, double* eps_out, int64_t* nx_out, int64_t* ny_out, bool general_only) {
@@ -1978,8 +2046,8 @@ int eb2_ksg_mi_pairs(int dev, const eb2_col_t* cols, int nvar, const int32_t* pa
 }
 
 // ---- a2: Frenzel-Pompe ----------------------------------------------------------------------------
-static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, int64_t row_lo, int64_t row_hi,
-                         double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+static int cmi_rows_once(int dev, const Input& in, int64_t n, int c_dim, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out, bool general_only) {
   const uint32_t flags = in.flags;
   const int d = 2 + c_dim;
   return guarded(dev, [&](Ctx& c) {
@@ -1987,8 +2055,36 @@ static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, 
     CallInit ci = begin_call(s);
     const double* raw = stage_input(s, in, d, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    bool plan_ok = false;
+    const k2::Plan plan = k2::make_plan3(n, d, &plan_ok);
+    if (plan_ok && !general_only && prune && c_dim >= 2 && d <= k2::kG3MaxD && k + 1 <= 8 && row_lo == 0 && row_hi == n &&
+        n >= g3_min_rows(d) && !getenv("EB2_NO_G3") && getenv("EB2_G3_CMI")) {
+      // (opt-in: measured at N = 2*10^5, c = 3 the grid examines 6 x fewer candidates than the general path but walks them
+      //  one thread per query and comes out slower, 12.5 against 5.7 ms; the counts tie.  Kept for the parity tests.)
+      // three-level grid over the condition: every space on this path (xyz, xz, yz, z) contains z, so ONE grid on
+      // (z_0, z_1[, z_2]) serves the search in the joint space and the three counts; x and y travel as payload
+      const double* rows[k2::kG3MaxD];
+      for (int t = 0; t < c_dim; ++t) rows[t] = raw + static_cast<int64_t>(2 + t) * n;
+      rows[c_dim] = raw;
+      rows[c_dim + 1] = raw + n;
+      G3Run g = run_g3(s, plan, rows, d, c_dim >= 3 ? 3 : 2, n, k, c_dim, ci);
+      mark(s, 3);
+      double* out4 = run_psi(s, PSI_AB_MINUS_C, g.host.cnt_row[1], g.host.cnt_row[2], g.host.cnt_row[0], nullptr, g.rows);
+      mark(s, 4);
+      if (eps_out) CU(cudaMemcpyAsync(eps_out, g.host.eps_row, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+      int64_t* outs[3] = {nz_out, nxz_out, nyz_out};
+      for (int i = 0; i < 3; ++i) {
+        if (!outs[i]) continue;
+        long long* wide = s.dev<long long>(n);
+        widen_kernel<<<cdiv(n, 256), 256, 0, c.stream>>>(g.host.cnt_row[i], wide, n);
+        s.launches++;
+        CU(cudaMemcpyAsync(outs[i], wide, sizeof(long long) * n, cudaMemcpyDeviceToHost, c.stream));
+      }
+      return finish_call(s, out4, ci.pairs, ci.nonfinite, n, partial);
+    }
     // every space on this path (xyz, xz, yz, z) contains z_0: sort by it
     // ... and, with a condition of 2+ dimensions, order the slots inside each chunk by z_1 (two-level layout)
+    c.last_pipeline = 0;
     PointSet ps = build_point_set(s, raw, d, n, nullptr, {}, prune ? 2 : -1, c_dim >= 2 ? d : 0, c_dim >= 2 ? 3 : -1);
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
@@ -2012,6 +2108,13 @@ static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, 
     export_outputs(s, ps, eps, cnts, o);
     return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
   });
+}
+
+static int cmi_rows_impl(int dev, const Input& in, int64_t n, int c_dim, int k, int64_t row_lo, int64_t row_hi,
+                         double* partial, double* eps_out, int64_t* nxz_out, int64_t* nyz_out, int64_t* nz_out) {
+  const int rc = cmi_rows_once(dev, in, n, c_dim, k, row_lo, row_hi, partial, eps_out, nxz_out, nyz_out, nz_out, false);
+  if (rc != EB2_ERR_RETRY_GENERAL) return rc;
+  return cmi_rows_once(dev, in, n, c_dim, k, row_lo, row_hi, partial, eps_out, nxz_out, nyz_out, nz_out, true);
 }
 
 int eb2_cmi_rows(int dev, const double* coords, int64_t n, int c_dim, int k, uint32_t flags, int64_t row_lo,
@@ -2160,15 +2263,28 @@ int eb2_ross_cmi(int dev, const double* coords, const int32_t* cls, int64_t n, i
 }
 
 // ---- a5: k-NN entropy ---------------------------------------------------------------------------------
-int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, int64_t row_lo,
-                     int64_t row_hi, double* partial, double* dist_out) {
-  if (int rc0 = check_common(coords, n, m, k)) return rc0;
-  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+static int entropy_rows_once(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, int64_t row_lo,
+                             int64_t row_hi, double* partial, double* dist_out, bool general_only) {
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CallInit ci = begin_call(s);
     const double* raw = stage_coords(s, coords, m, n, flags, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
+    bool plan_ok = false;
+    const k2::Plan plan = k2::make_plan3(n, m, &plan_ok);
+    if (plan_ok && !general_only && prune && m >= 3 && m <= k2::kG3MaxD && k + 1 <= 8 && row_lo == 0 && row_hi == n &&
+        n >= g3_min_rows(m) && !getenv("EB2_NO_G3")) {
+      // three-level grid: buckets of coordinate 0, cells over coordinates 1 and 2
+      const double* rows[k2::kG3MaxD];
+      for (int t = 0; t < m; ++t) rows[t] = raw + static_cast<int64_t>(t) * n;
+      G3Run g = run_g3(s, plan, rows, m, 3, n, k, 0, ci);
+      mark(s, 3);
+      double* out4 = run_psi(s, LOG_DIST, nullptr, nullptr, nullptr, g.host.eps_row, g.rows);     // :42, rows in the caller's order
+      mark(s, 4);
+      if (dist_out) CU(cudaMemcpyAsync(dist_out, g.host.eps_row, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+      return finish_call(s, out4, ci.pairs, ci.nonfinite, n, partial);
+    }
+    c.last_pipeline = 0;
     PointSet ps = build_point_set(s, raw, m, n, nullptr, {}, prune ? 0 : -1, m, m >= 2 ? 1 : -1);
     TileSet self = make_tiles(s, ps, row_lo, row_hi, true, 0, 0);
     mark(s, 1);
@@ -2183,6 +2299,15 @@ int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uin
     export_outputs(s, ps, dist, cnts, o);
     return finish_call(s, out4, ci.pairs, ci.nonfinite, self.rows, partial);
   });
+}
+
+int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, int64_t row_lo,
+                     int64_t row_hi, double* partial, double* dist_out) {
+  if (int rc0 = check_common(coords, n, m, k)) return rc0;
+  if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
+  const int rc = entropy_rows_once(dev, coords, n, m, k, flags, row_lo, row_hi, partial, dist_out, false);
+  if (rc != EB2_ERR_RETRY_GENERAL) return rc;
+  return entropy_rows_once(dev, coords, n, m, k, flags, row_lo, row_hi, partial, dist_out, true);
 }
 
 int eb2_entropy_finish(const double* partial, int64_t n, int m, int k, double* value) {

@@ -144,8 +144,9 @@ EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, in
  * ms[0] total device span (first H2D to last D2H), ms[1] k-NN kernel, ms[2] marginal counting,
  * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
 EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
-/* 1 when the last eb2_ksg_mi* call on `dev` ran on the bivariate pipeline (sort-free grid), 0 when the general path
- * took it (size / k / flags outside the pipeline, or a bucket overflow on heavily tied data), -1 without a context */
+/* which implementation the last estimator call on `dev` ran on: 1 = the bivariate pipeline (eb2_ksg_mi*), 2 = the
+ * three-level grid (eb2_entropy*, eb2_cmi* in 3+ dimensions), 0 = the general path (size / k / flags outside the grids, or
+ * a bucket overflow on heavily tied data), -1 without a context */
 EB2_API int eb2_last_pipeline(int dev);
 
 /* ---- device-resident columns (lag sweeps and pairwise_mi upload every

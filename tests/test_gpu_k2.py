@@ -195,3 +195,22 @@ def test_general_path_takes_over_when_a_bucket_overflows(monkeypatch):
     for key in ("eps", "nx", "ny"):
         assert np.array_equal(got[key], want[key]), key
     assert close(v, want["value"])
+
+
+def test_full_deferral_list_loses_nothing(monkeypatch):
+    """More deferred queries than the list holds (forced here by shrinking it): the queries that do not fit are finished
+    by the search kernel itself, the ones that fit by the leftover kernel, none twice and none never - run after run
+    (the reservations race; the count of the list must not be taken back)."""
+    monkeypatch.setenv("EB2_K2_LEFTCAP", "40")
+    rng = np.random.default_rng(21)
+    x = rng.standard_cauchy(6_000); y = x + rng.standard_cauchy(6_000)
+    co = nat.pack_coords([x, y])
+    vb, b = nat.ksg_mi(co, 3, flags=BRUTE, details=True)
+    for _ in range(25):
+        v, d = nat.ksg_mi(co, 3, details=True)
+        assert nat.last_pipeline() == 1
+        for key in ("eps", "nx", "ny"):
+            assert np.array_equal(d[key], b[key]), key
+        assert close(v, vb)
+    t = rng.standard_t(2, size=(60_000, 2))
+    same_as_brute(np.ascontiguousarray(t[:, 0]), np.ascontiguousarray(t[:, 1]), 3)

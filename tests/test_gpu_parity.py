@@ -238,6 +238,19 @@ def test_full_size_other_configs():
     assert np.array_equal(parts["dist"], want["dist"]) and close(value, want["value"])
 
 
+
+def same(got, want, keys, tag, gpu_again=None, oracle_again=None):
+    """Bit-equality of the per-row outputs; on a mismatch the message says where, and whether a repeat of the GPU call or
+    of the oracle call gives the same answer again (an unstable side shows up as a non-zero count)."""
+    for key in keys:
+        bad = np.flatnonzero(np.asarray(got[key]) != np.asarray(want[key]))
+        if bad.size:
+            rep_gpu = [int(np.sum(gpu_again()[key] != want[key])) for _ in range(3)] if gpu_again else None
+            rep_orc = int(np.sum(oracle_again()[key] != want[key])) if oracle_again else None
+            raise AssertionError((tag, key, int(bad.size), bad[:8].tolist(), np.asarray(got[key])[bad[:8]].tolist(),
+                                  np.asarray(want[key])[bad[:8]].tolist(), "gpu repeats vs want", rep_gpu, "oracle repeat vs want", rep_orc))
+
+
 @pytest.mark.parametrize("n", [2, 5, 16, 17, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2049])
 def test_tile_and_chunk_boundary_sizes(n):
     """Sizes around the 16-slot padding, the 256/512-row tiles and the 512-slot chunks, for the 2-D
@@ -249,14 +262,17 @@ def test_tile_and_chunk_boundary_sizes(n):
     want = oracle.ksg_mi(x, y, k, backend="c")
     for flags in (0, nat.FLAG_NO_PRUNE):
         value, parts = nat.ksg_mi(nat.pack_coords([x, y]), k, flags=flags, details=True)
-        assert all(np.array_equal(parts[key], want[key]) for key in ("eps", "nx", "ny")), (n, flags)
+        same(parts, want, ("eps", "nx", "ny"), ("ksg", n, flags), lambda: nat.ksg_mi(nat.pack_coords([x, y]), k, flags=flags, details=True)[1],
+             lambda: oracle.ksg_mi(x, y, k, backend="c"))
         assert close(value, want["value"])
     assert np.array_equal(nat.entropy(nat.pack_coords([x]), k, details=True)[1]["dist"], oracle.kth_distance(x, k, backend="c"))
     if n > 4:
         z = rng.normal(size=(n, 3))
         wc = oracle.conditional_mi(x, y, z, k, backend="c")
         vc, pc = nat.cmi(nat.pack_coords([x, y, z]), k, details=True)
-        assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"])
+        same(pc, wc, ("eps", "nxz", "nyz", "nz"), ("cmi", n), lambda: nat.cmi(nat.pack_coords([x, y, z]), k, details=True)[1],
+             lambda: oracle.conditional_mi(x, y, z, k, backend="c"))
+        assert close(vc, wc["value"])
 
 
 @pytest.mark.parametrize("kind", ["cauchy", "outlier", "x_ties", "clusters", "lattice", "sorted_input"])
@@ -287,7 +303,9 @@ def test_hard_distributions(kind):
     z = np.column_stack((y, x * 0.5 + rng.normal(size=n)))
     wc = oracle.conditional_mi(x, y, z, 3, backend="c")
     vc, pc = nat.cmi(nat.pack_coords([x, y, z]), 3, details=True)
-    assert all(np.array_equal(pc[key], wc[key]) for key in ("eps", "nxz", "nyz", "nz")) and close(vc, wc["value"]), kind
+    same(pc, wc, ("eps", "nxz", "nyz", "nz"), ("cmi", kind), lambda: nat.cmi(nat.pack_coords([x, y, z]), 3, details=True)[1],
+         lambda: oracle.conditional_mi(x, y, z, 3, backend="c"))
+    assert close(vc, wc["value"]), kind
 
 
 def test_ragged_classes():
