@@ -14,7 +14,8 @@ Numbers on the JSON line:
   value      estimates/s with the coordinates already resident in HBM (C ABI, EB2_FLAG_DEVICE_INPUT)
   e2e        the same metric through the public API ``ennemi_b200.estimate_mi(y, x, k=3)`` on HOST
              numpy buffers: host preprocessing + H2D + kernels + D2H inside the timed region
-  roofline   the dominant kernel (knn_kernel<2,4>) against the MEASURED FP64 issue rate
+  roofline   the dominant kernel (knn_kernel2<4> + its leftover kernel, the k-NN search of the bivariate pipeline)
+             against the MEASURED FP64 issue rate
   brute_force  the same step with EB2_FLAG_NO_PRUNE (every candidate tile visited): the kernel the
              FP64 roofline in SURVEY.md §8(d) is defined on
   cpu_baseline  the reference's CPU path (same SciPy cKDTree calls, via oracle/) on a bounded sample
@@ -44,9 +45,10 @@ K_NEIGH = 3
 RHO = 0.6
 FP64_OPS_PER_PAIR = 4          # 2-D space: 2 subtractions + 2 compares (2d per pair)
 SAMPLE_STRIDE = 50             # CPU baseline: every 50th row is queried, trees hold all rows
-# dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel<2,4> at this workload, one ncu --set full capture
-# (profiles/ncu_r01_summary.md): the 16 MB point set is read once, everything else stays in the 126 MB L2
-NCU_DRAM_BYTES_PER_LAUNCH = 16.7e6
+# dram__bytes_read.sum + dram__bytes_write.sum of knn_kernel2<4> at this workload, one ncu --set full capture
+# (profiles/ncu_r02_summary.md: 22.0 MB read, 0.5 kB written; leftover_kernel2<4> adds 3.0 MB): the slot-ordered point
+# set (16 MB) and the cell table (4 MB) are read once, everything else stays in the 126 MB L2
+NCU_DRAM_BYTES_PER_LAUNCH = 22.0e6
 # the workload both arms (`--impl ours` / `--impl reference`) run: identical `config` on both JSON lines
 CONFIG = {"workload": "estimate_mi bivariate Gaussian rho=0.6, N=1,000,000, k=3 (BASELINE.json configs[1]); a step = one "
                       "complete estimate per GPU", "n": N_ROWS, "k": K_NEIGH, "rho": RHO, "seed": 0}
@@ -534,7 +536,7 @@ def run_gpu(args):
         "config": dict(CONFIG),
         "details": {"step": "N > 1: independent same-shape batches fanned out, one estimate per GPU per step, no collective; the "
                             "row-sharded single estimate is in `sharded`",
-                    "algorithm": "exact two-level search (bit-exact eps and counts); brute force in brute_force",
+                    "algorithm": "exact search on a sort-free adaptive grid (bit-exact eps and counts); brute force in brute_force",
                     "l2": "flushed between steps (512 MiB write); inputs are 16 MB",
                     "parallelism": "single GPU" if world == 1 else f"task fan-out x{world} (+ rows/{world} in `sharded`)"},
         "mi": last["value"] if world == 1 else last["value_own"],
@@ -546,17 +548,18 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "phase_ms": phases,
         "layout_roofline": layout_roofline(phases),
-        "roofline": {"bound": "fp64", "kernel": "knn_kernel<2,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp64", "kernel": "knn_kernel2<4> + leftover_kernel2<4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
                      "survey_8d_frac": (float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR) / (knn_per_ms * 1e-3) * 1e-12 / peak,
                      "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
                              "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
-                             "ops = pairs actually evaluated x 4 (k-NN main + leftover kernels, ms_per_launch = both); the default search "
-                             "looks at ~30 candidates per row (per-lane windows of the in-chunk coordinate) and is bound by shared-memory "
-                             "latency and per-chunk synchronisation, not by FP64 issue - survey_8d_frac is the same time against "
-                             "SURVEY.md 8(d)'s brute-force count N^2 x 4, which a pruned algorithm legitimately exceeds; the FP64 "
-                             "roofline proper (every pair evaluated) is in brute_force"},
+                             "ops = candidate pairs actually examined x 4 (search + leftover kernels, ms_per_launch = both, CUDA events "
+                             "on the launching stream); the grid search examines ~25 candidates per row, one thread per query, and is "
+                             "bound by instruction issue of the walk itself (62 % issue-active, 15.5 of 32 lanes active: "
+                             "profiles/ncu_r02_summary.md), not by FP64 throughput - survey_8d_frac is the same time against SURVEY.md "
+                             "8(d)'s brute-force count N^2 x 4, which a pruned algorithm legitimately exceeds; the FP64 roofline proper "
+                             "(every pair evaluated) is in brute_force; traffic = dram bytes of knn_kernel2<4> per launch (ncu)"},
         "clocks": clocks,
     }
     if e2e_extra:
@@ -583,11 +586,13 @@ def run_gpu(args):
 
 
 def layout_roofline(phases):
-    """The sort/partition phase against the HBM roofline (radix sorts count as bytes).  Algorithmic
-    bytes of one step: two 64-bit key + 32-bit index radix sorts (8 passes, each reads and writes 12 B per row), the
-    2-pass 32-bit chunk partition (8 B per row per pass, both ways) and the gather of two coordinate rows + row map."""
+    """The grid-build phase on the critical path against the HBM roofline.  Algorithmic bytes of one step on the main
+    stream: x column into buckets (histogram: 8 B value read + 2 B bucket id written; scatter: 2 + 8 read, 4 B row + 8 B
+    value written = 32 B/row) and the layout kernel (4 B row + 8 B x + 8 B y read, x, y, row, bucket id and cell table
+    written = 46 B/row).  The y column's buckets and both columns' fine cells (another 72 B/row) are built on the second
+    stream underneath the search and are not in `layout_ms`."""
     n = float(N_ROWS)
-    bytes_step = 2 * 8 * 2 * 12 * n + 2 * 2 * 8 * n + (2 * 8 + 4) * 2 * n
+    bytes_step = (32 + 46) * n
     peak, src = 6528.0, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -596,10 +601,11 @@ def layout_roofline(phases):
         pass
     ms = phases.get("layout_ms") or float("nan")
     achieved = bytes_step / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "phase": "layout (x and y radix sorts, chunk partition, gather)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "bytes_per_step": bytes_step, "ms": ms, "peak_source": src,
-            "note": "at N = 1e6 every radix pass is a ~17 us kernel of 174 CTAs: latency bound (decoupled look-back chain), the "
-                    "working set lives in L2; listed because this phase is now the largest of the default step"}
+    return {"bound": "hbm", "phase": "grid build on the critical path (x buckets: sample, rank, splitters, histogram, scatter; layout)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "bytes_per_step": bytes_step, "ms": ms,
+            "peak_source": src,
+            "note": "seven short kernels (5-64 us each, the 16 MB working set lives in L2): bound by launch latency and the "
+                    "dependent chain sample -> splitters -> histogram -> scatter -> layout, not by HBM"}
 
 
 _REAL_STDOUT = None

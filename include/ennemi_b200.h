@@ -145,8 +145,8 @@ EB2_API int eb2_ball_count(int dev, const double* coords, const int32_t* cls, in
  * ms[3] digamma/reduction, ms[4] sort/permutation.  launches = kernels launched by that call. */
 EB2_API int eb2_last_timing(int dev, double* ms, int* launches);
 /* which implementation the last estimator call on `dev` ran on: 1 = the bivariate pipeline (eb2_ksg_mi*), 2 = the
- * three-level grid (eb2_entropy*, eb2_cmi* in 3+ dimensions), 0 = the general path (size / k / flags outside the grids, or
- * a bucket overflow on heavily tied data), -1 without a context */
+ * three-level grid (eb2_entropy* in 3 and 4 dimensions from 200,000 rows on; eb2_cmi* only with EB2_G3_CMI set), 0 = the
+ * general path (size / k / flags outside the grids, or a bucket overflow on heavily tied data), -1 without a context */
 EB2_API int eb2_last_pipeline(int dev);
 
 /* ---- device-resident columns (lag sweeps and pairwise_mi upload every

@@ -28,3 +28,17 @@ print("entropy", nat.entropy(nat.pack_coords([z]), 3))
 cls = rng.integers(0, 5, n).astype(np.int32)
 print("ross", nat.ross_mi(nat.pack_coords([d[:, 0]]), cls, 5, 3))
 print("ross cmi", nat.ross_cmi(nat.pack_coords([d[:, 0], z]), cls, 5, 3))
+print("entropy 1-d (two-pointer k-NN)", nat.entropy(nat.pack_coords([d[:, 0]]), 3))
+# three-level grid (forced onto a small input), entropy and the opt-in Frenzel-Pompe variant
+os.environ["EB2_G3_MIN"] = "2"; os.environ["EB2_G3_CMI"] = "1"
+x4 = rng.standard_t(3, size=(n, 4))
+print("grid entropy 4-d", nat.entropy(nat.pack_coords([x4]), 5, details=True)[0], nat.last_pipeline())
+print("grid entropy 3-d", nat.entropy(nat.pack_coords([x4[:, :3]]), 3), nat.last_pipeline())
+z3 = rng.normal(size=(n, 3))
+print("grid cmi c=3", nat.cmi(nat.pack_coords([d[:, 0], d[:, 1], z3]), 3, details=True)[0], nat.last_pipeline())
+del os.environ["EB2_G3_MIN"]; del os.environ["EB2_G3_CMI"]
+# a full deferral list in the bivariate pipeline
+os.environ["EB2_K2_LEFTCAP"] = "40"
+c2 = rng.standard_cauchy(size=(6_000, 2))
+print("full deferral list", nat.ksg_mi(nat.pack_coords([c2[:, 0], c2[:, 0] + c2[:, 1]]), 3, details=True)[0], nat.last_pipeline())
+del os.environ["EB2_K2_LEFTCAP"]
