@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from ennemi_b200 import _native as nat
+if os.environ.get("EB2_LIB"):
+    nat.LIB_PATH = os.path.abspath(os.environ["EB2_LIB"])          # a build variant (developer experiments)
 
 rng = np.random.default_rng(0)
 for n in (1_000_000, 100_000):
