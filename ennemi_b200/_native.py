@@ -31,7 +31,7 @@ EXPORTS = (
     "eb2_ksg_mi", "eb2_ksg_mi_rows", "eb2_ksg_mi_finish",
     "eb2_cmi", "eb2_cmi_rows", "eb2_cmi_finish",
     "eb2_ross_mi", "eb2_ross_cmi",
-    "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish",
+    "eb2_entropy", "eb2_entropy_rows", "eb2_entropy_finish", "eb2_entropy_cols",
     "eb2_psi", "eb2_kth_distance", "eb2_ball_count", "eb2_last_timing", "eb2_measure_fp64_peak",
     "eb2_cache_put", "eb2_cache_drop", "eb2_ksg_mi_cols", "eb2_cmi_cols", "eb2_last_data_flags",
     "eb2_mi_cols_batch", "eb2_ksg_mi_cols_rows", "eb2_cmi_cols_rows", "eb2_cache_stats",
@@ -97,6 +97,7 @@ def load():
         lib.eb2_cache_stats_many.argtypes = [_int, _vp, _vp, _int, _i64, _i64, _vp, _vp]
         lib.eb2_ksg_mi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _c_dp]
         lib.eb2_cmi_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
+        lib.eb2_entropy_cols.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _c_dp]
         lib.eb2_ksg_mi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _u32, _i64, _i64, _c_dp]
         lib.eb2_cmi_cols_rows.argtypes = [_int, ctypes.POINTER(ColDesc), _i64, _int, _int, _u32, _i64, _i64, _c_dp]
         lib.eb2_cache_stats.argtypes = [_int, ctypes.c_uint64, _i64, _i64, _i64, _c_dp, _c_dp]
@@ -438,6 +439,11 @@ def ksg_mi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
 def cmi_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
     """Frenzel-Pompe CMI of cached device columns (``cols``: x, y, then the condition's columns)."""
     return _cols_call(load().eb2_cmi_cols, cols, dev, n, len(cols) - 2, k, flags)
+
+
+def entropy_cols(cols, n: int, k: int, dev: int = 0, flags: int = 0) -> float:
+    """k-NN entropy of the space spanned by cached device columns (``std = 0`` descriptors: values as they are)."""
+    return _cols_call(load().eb2_entropy_cols, cols, dev, n, len(cols), k, flags)
 
 
 def mi_cols_batch(tasks, n: int, k: int, dev: int = 0, flags: int = 0):

@@ -16,7 +16,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from . import _align, _checks, _columns, _estimators as est, _schedule
+from . import _align, _checks, _columns, _devices, _estimators as est, _native, _schedule
 from ._align import MiTask
 from ._columns import ColsTask
 
@@ -82,15 +82,18 @@ def estimate_entropy(x, *, k: int = 3, multidim: bool = False, discrete: bool = 
         cond_arr = np.asarray(cond)
         _checks.cond_is_valid(cond_arr, x_arr.shape[0])
         # chain rule, no bias correction: H(X | C) = H(X, C) - H(C)
-        h_cond = _entropy_of(cond_arr, k, True, mask, discrete, drop_nan)
-        if multidim or x_arr.ndim == 1:
-            joint = _entropy_rows(np.column_stack((x_arr, cond_arr)), k, mask, discrete, drop_nan)
-            result = np.asarray(joint - h_cond)
+        if _cond_entropy_on_device(x_arr, cond_arr, mask, discrete, drop_nan):
+            result = _cond_entropy_device(x_arr, cond_arr, k, multidim)
         else:
-            joint = np.empty(x_arr.shape[1])
-            for j in range(x_arr.shape[1]):
-                joint[j] = _entropy_rows(np.column_stack((x_arr[:, j], cond_arr)), k, mask, discrete, drop_nan)
-            result = joint - h_cond
+            h_cond = _entropy_of(cond_arr, k, True, mask, discrete, drop_nan)
+            if multidim or x_arr.ndim == 1:
+                joint = _entropy_rows(np.column_stack((x_arr, cond_arr)), k, mask, discrete, drop_nan)
+                result = np.asarray(joint - h_cond)
+            else:
+                joint = np.empty(x_arr.shape[1])
+                for j in range(x_arr.shape[1]):
+                    joint[j] = _entropy_rows(np.column_stack((x_arr[:, j], cond_arr)), k, mask, discrete, drop_nan)
+                result = joint - h_cond
 
     pd = _pandas()
     if not multidim and pd is not None:
@@ -99,6 +102,48 @@ def estimate_entropy(x, *, k: int = 3, multidim: bool = False, discrete: bool = 
         if isinstance(x, pd.Series):
             return pd.DataFrame(np.atleast_2d(result), columns=[x.name])
     return result
+
+
+def _cond_entropy_on_device(x_arr, cond_arr, mask, discrete: bool, drop_nan: bool) -> bool:
+    """Whether H(X | cond) runs on device-resident columns: continuous float64 data, every row used, large enough for
+    the uploads to matter, one process per estimate (a row-sharded job keeps its own route)."""
+    if discrete or mask is not None or x_arr.shape[0] < DEVICE_COLUMNS_MIN_ROWS:
+        return False
+    if x_arr.dtype != np.float64 or cond_arr.dtype != np.float64 or x_arr.ndim > 2 or cond_arr.ndim > 2:
+        return False
+    if drop_nan and (np.isnan(x_arr).any() or np.isnan(cond_arr).any()):
+        return False                                  # (rows are dropped per variable: different row sets)
+    from . import distributed
+    return not distributed.row_sharding_enabled()
+
+
+def _cond_entropy_device(x_arr: np.ndarray, cond_arr: np.ndarray, k: int, multidim: bool):
+    """H(X_j | C) = H(X_j, C) - H(C) (``_driver.py:202-220``) with every column of X and C uploaded ONCE: the columns of C
+    are named in both terms of every variable instead of being stacked and copied again per term.
+    Same checks, in the reference's order (``_driver.py:180-200``)."""
+    n = x_arr.shape[0]
+    if k >= n:
+        raise ValueError(_checks.MSG_K_TOO_LARGE)
+    if np.isnan(cond_arr).any() or np.isnan(x_arr).any():
+        raise ValueError(_checks.MSG_NANS_LEFT)
+    dev = _devices.current()
+    store = _columns.ColumnStore()
+    try:
+        xkeys = store.add_columns(x_arr)
+        ckeys = store.add_columns(cond_arr)
+        for key in xkeys + ckeys:
+            store.ensure(dev, key)
+
+        def desc(key):
+            return _native.ColDesc(key, 0, 1, 0.0, 0.0, 0, 0, 1)          # std = 0: the values as they are
+
+        cdesc = [desc(key) for key in ckeys]
+        h_cond = _native.entropy_cols(cdesc, n, k, dev=dev)
+        if multidim or x_arr.ndim == 1:
+            return np.asarray(_native.entropy_cols([desc(key) for key in xkeys] + cdesc, n, k, dev=dev) - h_cond)
+        return np.array([_native.entropy_cols([desc(key)] + cdesc, n, k, dev=dev) for key in xkeys]) - h_cond
+    finally:
+        store.close()
 
 
 def _entropy_rows(rows: np.ndarray, k: int, mask, discrete: bool, drop_nan: bool) -> float:

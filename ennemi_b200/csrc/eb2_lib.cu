@@ -2263,12 +2263,13 @@ int eb2_ross_cmi(int dev, const double* coords, const int32_t* cls, int64_t n, i
 }
 
 // ---- a5: k-NN entropy ---------------------------------------------------------------------------------
-static int entropy_rows_once(int dev, const double* coords, int64_t n, int m, int k, uint32_t flags, int64_t row_lo,
+static int entropy_rows_once(int dev, const Input& in, int64_t n, int m, int k, int64_t row_lo,
                              int64_t row_hi, double* partial, double* dist_out, bool general_only) {
+  const uint32_t flags = in.flags;
   return guarded(dev, [&](Ctx& c) {
     Scratch s(c);
     CallInit ci = begin_call(s);
-    const double* raw = stage_coords(s, coords, m, n, flags, ci.nonfinite);
+    const double* raw = stage_input(s, in, m, n, ci.nonfinite);
     const bool prune = !(flags & EB2_FLAG_NO_PRUNE);
     bool plan_ok = false;
     const k2::Plan plan = k2::make_plan3(n, m, &plan_ok);
@@ -2305,9 +2306,23 @@ int eb2_entropy_rows(int dev, const double* coords, int64_t n, int m, int k, uin
                      int64_t row_hi, double* partial, double* dist_out) {
   if (int rc0 = check_common(coords, n, m, k)) return rc0;
   if (!partial) return fail(EB2_ERR_ARG, "partial is NULL");
-  const int rc = entropy_rows_once(dev, coords, n, m, k, flags, row_lo, row_hi, partial, dist_out, false);
+  Input in; in.coords = coords; in.flags = flags;
+  const int rc = entropy_rows_once(dev, in, n, m, k, row_lo, row_hi, partial, dist_out, false);
   if (rc != EB2_ERR_RETRY_GENERAL) return rc;
-  return entropy_rows_once(dev, coords, n, m, k, flags, row_lo, row_hi, partial, dist_out, true);
+  return entropy_rows_once(dev, in, n, m, k, row_lo, row_hi, partial, dist_out, true);
+}
+
+// the same estimate on device-resident columns (H(X | C) = H(X, C) - H(C), _driver.py:202-220, uploads
+// every column of X and C once and names them in both terms)
+int eb2_entropy_cols(int dev, const eb2_col_t* cols, int64_t n, int m, int k, uint32_t flags, double* value) {
+  if (!cols || !value) return fail(EB2_ERR_ARG, "cols/value is NULL");
+  if (int rc0 = check_common(reinterpret_cast<const double*>(cols), n, m, k)) return rc0;
+  Input in; in.cols = cols; in.flags = flags & ~EB2_FLAG_DEVICE_INPUT;
+  double partial[EB2_P_LEN];
+  int rc = entropy_rows_once(dev, in, n, m, k, 0, n, partial, nullptr, false);
+  if (rc == EB2_ERR_RETRY_GENERAL) rc = entropy_rows_once(dev, in, n, m, k, 0, n, partial, nullptr, true);
+  if (rc) return rc;
+  return eb2_entropy_finish(partial, n, m, k, value);
 }
 
 int eb2_entropy_finish(const double* partial, int64_t n, int m, int k, double* value) {

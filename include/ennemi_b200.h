@@ -187,6 +187,10 @@ typedef struct eb2_col {
  * eb2_last_data_flags() tells NaN input (bit0) from otherwise non-finite prepared data (bit1). */
 EB2_API int eb2_ksg_mi_cols(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags, double* value);
 EB2_API int eb2_cmi_cols(int dev, const eb2_col_t* cols, int64_t n, int c, int k, uint32_t flags, double* value);
+/* k-NN entropy of m device-resident columns (a5 on cached columns): the conditional entropy
+ * H(X | C) = H(X, C) - H(C) of ennemi/_driver.py:202-220 uploads X and C once and names the columns of C in both terms
+ * (SURVEY.md 8 f4).  std = 0 in a descriptor passes the values through unscaled, as estimate_entropy does. */
+EB2_API int eb2_entropy_cols(int dev, const eb2_col_t* cols, int64_t n, int m, int k, uint32_t flags, double* value);
 /* ... and with query rows sharded (partial block as in eb2_*_rows; finish with eb2_*_finish) */
 EB2_API int eb2_ksg_mi_cols_rows(int dev, const eb2_col_t* cols, int64_t n, int k, uint32_t flags,
                                  int64_t row_lo, int64_t row_hi, double* partial);

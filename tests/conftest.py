@@ -41,7 +41,7 @@ class OracleBackend:
 
     PATCHED = ("ksg_mi", "cmi", "ross_mi", "ross_cmi", "entropy", "psi",
                "cache_put", "cache_drop", "ksg_mi_cols", "cmi_cols", "mi_cols_batch", "cache_stats",
-               "cache_put_block", "cache_stats_many", "ksg_mi_pairs")
+               "cache_put_block", "cache_stats_many", "ksg_mi_pairs", "entropy_cols")
 
     def __init__(self, backend="scipy"):
         import oracle
@@ -141,6 +141,10 @@ class OracleBackend:
 
     def ksg_mi_pairs(self, cols, pairs, n, k, dev=0, flags=0):
         return self.mi_cols_batch([[cols[i], cols[j]] for i, j in np.asarray(pairs).reshape(-1, 2)], n, k, dev, flags)
+
+    def entropy_cols(self, descs, n, k, dev=0, flags=0):
+        rows = self._gather(descs, n, dev, flags)
+        return self.o.knn_entropy(np.column_stack(rows), k, backend=self.backend)["value"]
 
     def cmi_cols(self, descs, n, k, dev=0, flags=0):
         rows = self._gather(descs, n, dev, flags)

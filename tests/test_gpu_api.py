@@ -313,3 +313,31 @@ def test_cmi_lag_sweep_full_size_vs_reference_calls():
             for key in ("eps", "nxz", "nyz", "nz"):
                 assert np.array_equal(parts[key], want[key]), key
             assert abs(value - got[lag, 0]) <= 1e-13
+
+
+def test_conditional_entropy_on_device_columns_gpu(monkeypatch):
+    """estimate_entropy(x, cond=...) on device-resident columns (eb2_entropy_cols): the same bits as the
+    host route through eb2_entropy, and the reference's chain rule on SciPy's k-th distances within 1e-10."""
+    import oracle
+    from ennemi_b200 import api
+    rng = np.random.default_rng(12)
+    n = 30_000
+    c = rng.normal(size=(n, 2))
+    x = np.column_stack((c[:, 0] + rng.normal(size=n), rng.normal(size=n), c[:, 1] - 0.5 * rng.normal(size=n)))
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host = eb.estimate_entropy(x, cond=c)
+    host_md = eb.estimate_entropy(x, cond=c, multidim=True, k=5)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 20_000)
+    dev = eb.estimate_entropy(x, cond=c)
+    assert np.array_equal(dev, host)
+    assert np.array_equal(eb.estimate_entropy(x, cond=c, multidim=True, k=5), host_md)
+    assert np.array_equal(eb.estimate_entropy(x[:, 1], cond=c[:, 0]), eb.estimate_entropy(x[:, 1], cond=c[:, :1]))
+    h_c = oracle.knn_entropy(c, 3, backend="scipy")["value"]
+    for j in range(3):
+        want = oracle.knn_entropy(np.column_stack((x[:, j], c)), 3, backend="scipy")["value"] - h_c
+        assert abs(dev[j] - want) <= 1e-10, j
+    bad = x.copy(); bad[17, 2] = np.inf
+    with pytest.raises(ValueError, match="data must be finite"):
+        eb.estimate_entropy(bad, cond=c)
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_entropy(np.where(np.isinf(bad), np.nan, bad), cond=c)

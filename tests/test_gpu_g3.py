@@ -118,3 +118,31 @@ def test_against_the_reference_calls():
     want = oracle.knn_entropy(d4, 5, backend="scipy")
     v, got = nat.entropy(nat.pack_coords([d4]), 5, details=True)
     assert np.array_equal(got["dist"], want["dist"]) and close(v, want["value"])
+
+
+def test_default_dispatch_and_full_size_entropy(monkeypatch):
+    """Without the test knobs: 3-D and 4-D entropy take the grid from 200,000 rows on, smaller inputs, wider spaces and
+    Frenzel-Pompe stay on the general path; BASELINE.json configs[4] (4-D, N = 500,000, k = 5) against the reference's
+    SciPy calls, every row."""
+    import oracle
+    monkeypatch.delenv("EB2_G3_MIN")
+    monkeypatch.delenv("EB2_G3_CMI")
+    rng = np.random.default_rng(0)
+    n = 500_000
+    cov = np.array([[1.0, 0.5, 0.2, 0.1], [0.5, 1.0, 0.3, 0.0], [0.2, 0.3, 1.0, -0.4], [0.1, 0.0, -0.4, 1.0]])
+    d4 = rng.multivariate_normal(np.zeros(4), cov, size=n)
+    want = oracle.knn_entropy(d4, 5, backend="scipy")
+    v, got = nat.entropy(nat.pack_coords([d4]), 5, details=True)
+    assert nat.last_pipeline() == 2
+    assert np.array_equal(got["dist"], want["dist"]) and close(v, want["value"])
+    t = rng.standard_t(2, size=(200_000, 3))                  # heavy tails at the smallest size the grid takes
+    want = oracle.knn_entropy(t, 3, backend="scipy")
+    v, got = nat.entropy(nat.pack_coords([t]), 3, details=True)
+    assert nat.last_pipeline() == 2
+    assert np.array_equal(got["dist"], want["dist"]) and close(v, want["value"])
+    for x in (d4[:150_000], rng.normal(size=(200_000, 5))):
+        nat.entropy(nat.pack_coords([x]), 3)
+        assert nat.last_pipeline() == 0
+    z = d4[:200_000, :2]
+    nat.cmi(nat.pack_coords([d4[:200_000, 2], d4[:200_000, 3], z]), 3)
+    assert nat.last_pipeline() == 0

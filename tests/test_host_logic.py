@@ -351,3 +351,35 @@ def test_noise_stream_skip_keeps_the_draw_sequence():
     s3 = _align._NoiseStream()
     s3.skip((97,)); s3.skip((97,))
     assert np.array_equal(s3.normal((97, 3)), c)
+
+
+def test_conditional_entropy_on_device_columns(oracle_backend, golden_api, monkeypatch):
+    """H(X | C) on device-resident columns: X and C uploaded once each whatever the number of
+    variables, the columns of C named in both terms; same values as the host route (which stacks and copies C per
+    term) and as the fixtures of the unmodified reference; the reference's errors in the reference's words."""
+    from ennemi_b200 import api
+    g = golden_api
+    rng = np.random.default_rng(4)
+    n = 400
+    c = rng.normal(size=(n, 2))
+    x = np.column_stack((c[:, 0] + rng.normal(size=n), rng.normal(size=n), c[:, 1] - rng.normal(size=n)))
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host = eb.estimate_entropy(x, cond=c)
+    host_md = eb.estimate_entropy(x, cond=c, multidim=True)
+    host_1d = eb.estimate_entropy(x[:, 0], cond=c[:, 0], k=5)
+    puts0 = getattr(oracle_backend, "block_puts", 0)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    assert eq(eb.estimate_entropy(x, cond=c), host)
+    assert getattr(oracle_backend, "block_puts", 0) == puts0 + 2           # one upload of X, one of C, for three variables
+    assert eq(eb.estimate_entropy(x, cond=c, multidim=True), host_md)
+    assert eq(eb.estimate_entropy(x[:, 0], cond=c[:, 0], k=5), host_1d)
+    x3, cond = g["inputs"]["x3"], g["inputs"]["cond"]
+    assert eq(eb.estimate_entropy(x3[:, :2], cond=cond), g["ent_cond"]["out"])          # fixture of the unmodified reference
+    assert not oracle_backend.cache                                        # the store dropped its columns
+    xn = x.copy(); xn[3, 1] = np.nan
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_entropy(xn, cond=c)
+    with pytest.raises(ValueError, match="k must be smaller"):
+        eb.estimate_entropy(x[:3], cond=c[:3], k=3)
+    # rows dropped per variable, a mask, discrete data: the host route (identical to the reference's)
+    assert eq(eb.estimate_entropy(xn, cond=c, drop_nan=True)[[0, 2]], host[[0, 2]])
