@@ -551,6 +551,9 @@ def run_gpu(args):
         "roofline": {"bound": "fp64", "kernel": "knn_kernel2<4> + leftover_kernel2<4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "ops_per_launch": ops, "ms_per_launch": knn_per_ms,
+                     # what actually bounds the kernel, from the ncu capture of this workload (profiles/ncu_r02_summary.md)
+                     "ncu": {"issue_active_pct": 62.1, "lanes_active_per_instruction": 15.5, "warps_active_pct": 42.2,
+                             "dram_read_mb": 22.0, "registers": 64},
                      "survey_8d_frac": (float(N_ROWS) * N_ROWS * FP64_OPS_PER_PAIR) / (knn_per_ms * 1e-3) * 1e-12 / peak,
                      "note": "FP64 CUDA-core issue bound (DADD+DSETP, 1 op = 1 FP64 instruction per lane); peak = DADD "
                              "issue rate measured live by eb2_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 figure); "
