@@ -837,7 +837,8 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 // Three-level grid for spaces of three and more dimensions
 // =====================================================================================================================
 constexpr int kG3Threads = 256;
-constexpr int kG3Heavy = 48;          // cells in a bucket's window above which a query goes to the leftover kernel
+constexpr int kG3Heavy = 48;          // counts: cells in a bucket's window above which a query goes to the warp kernel
+                                      // (the search takes its limit as a launch argument: knn3)
 
 // ---- layout: the rows of every bucket of coordinate 0 grouped into C1 x C2 cells over its own ranges of coordinates 1, 2
 __global__ void __launch_bounds__(kG3Threads) layout3_kernel(const Col* col0, const Grid3* gp, long long n, int NB) {
@@ -978,7 +979,7 @@ constexpr int kG3Pre = 2;             // bounding pass: cells either side of the
 // from above.  Exact pass: a fresh list, gated by the next double above that bound, over the windows of every bucket
 // the gate reaches, nearest first, the gate tightening to the running k-th distance.  Every row within the true k-th
 // distance passes the gate and lies in the windows (monotone cell maps, thresholds widened by 2^-50), so the list ends
-// as the exhaustive search's: bit-exact.  Windows of more than kG3Heavy cells, or more than `near` buckets on a side,
+// as the exhaustive search's: bit-exact.  Windows of more than `heavy_cells` cells, or more than `near` buckets on a side,
 // are left to leftover3_kernel from that bucket on.
 template <int D, int K1T>
 __global__ void __launch_bounds__(kG3Threads) knn3_kernel(const Col* col0, const Grid3* gp, long long n, int NB, int k, int near,
@@ -1099,7 +1100,7 @@ __global__ void __launch_bounds__(kG3Threads) knn3_kernel(const Col* col0, const
   if (valid) {
     if (my_e >= 0) {
       LeftEnt le;
-      le.slot = slot; le.rstart = rstart; le.lend = lend; le.skip_a = heavy ? 1 : 0;
+      le.slot = slot; le.rstart = rstart; le.lend = lend; le.skip_a = 0;       // (no seeds to skip on this path)
       g.left[my_e] = le;
       g.eps[slot] = thr;                                 // the gate the leftover kernel starts from
 #pragma unroll
