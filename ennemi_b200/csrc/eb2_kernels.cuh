@@ -1019,6 +1019,8 @@ struct CountArgs {
   // chunk_len(C+E) slots, shared coordinate 1 inside each chunk; cell_lo/hi = range of coordinate 0 per chunk
   const double* cell_lo;
   const double* cell_hi;
+  int split;             // >= 1: the chunk range of every tile is dealt to this many CTAs, which ADD their counts
+                         // (outputs zeroed by the caller when split > 1): more, shorter work items for small sets
   int* cnt_s;            // out per query slot (C > 0)
   int* cnt_e0;           // out (E > 0)
   int* cnt_e1;           // out (E > 1)
@@ -1053,7 +1055,8 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
 #pragma unroll
   for (int t = 0; t < E; ++t) brows.row[C + t] = a.b_erow.row[t];
 
-  for (int tile_id = blockIdx.x; tile_id < a.ntiles; tile_id += gridDim.x) {
+  for (int work = blockIdx.x; work < a.ntiles * a.split; work += gridDim.x) {
+    const int tile_id = work / a.split, part = work - tile_id * a.split;
     const Tile tile = a.tiles[tile_id];
     double qs[QPT][CS];
     double qe[QPT][ES];
@@ -1213,6 +1216,12 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
     }
     unsigned long long npairs = 0;
     const bool dense_hits = a.prune_b_row >= 0 || cells;
+    if (a.split > 1 && ch_hi > ch_lo) {        // this CTA's share of the tile's chunk range
+      const int span = ch_hi - ch_lo;
+      const int lo = ch_lo + (int)((long long)span * part / a.split);
+      ch_hi = ch_lo + (int)((long long)span * (part + 1) / a.split);
+      ch_lo = lo;
+    }
 
     for (int j = ch_lo; j < ch_hi; ++j) {
       const int c_off = j * TC;
@@ -1305,9 +1314,15 @@ __global__ void __launch_bounds__(kThreads, knn_min_blocks(C + E, 2, QPT)) count
     for (int i = 0; i < QPT; ++i) {
       if (valid[i]) {
         const int slot = tile.q_lo + qslot[i];
-        if constexpr (C > 0) a.cnt_s[slot] = ns[i];
-        if constexpr (E > 0) a.cnt_e0[slot] = ne0[i];
-        if constexpr (E > 1) a.cnt_e1[slot] = ne1[i];
+        if (a.split > 1) {
+          if constexpr (C > 0) { if (ns[i]) atomicAdd(&a.cnt_s[slot], ns[i]); }
+          if constexpr (E > 0) { if (ne0[i]) atomicAdd(&a.cnt_e0[slot], ne0[i]); }
+          if constexpr (E > 1) { if (ne1[i]) atomicAdd(&a.cnt_e1[slot], ne1[i]); }
+        } else {
+          if constexpr (C > 0) a.cnt_s[slot] = ns[i];
+          if constexpr (E > 0) a.cnt_e0[slot] = ne0[i];
+          if constexpr (E > 1) a.cnt_e1[slot] = ne1[i];
+        }
       }
     }
     if (a.pairs) {

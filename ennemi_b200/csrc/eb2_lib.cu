@@ -650,7 +650,7 @@ void run_knn(Scratch& s, const PointSet& ps, const RowSel& rows, int D, int k, c
   a.defer_below = 0; a.left_list = nullptr; a.left_count = nullptr; a.left_best = nullptr;
   const int k1t = (k + 1 <= 4) ? 4 : 8;
   if (a.sort_row >= 0 && k + 1 <= 8) {
-    a.defer_below = a.cell_lo ? (D <= 2 ? 4 : 8) : 16;      // measured optima (tools/exp_defer.py, tools/exp_knobs.py)
+    a.defer_below = a.cell_lo ? (D <= 2 ? 4 : 8) : 16;      // measured optima (round 1 sweeps of EB2_DEFER)
     if (const char* e = getenv("EB2_DEFER")) a.defer_below = atoi(e);     // tuning knob
   }
   if (a.defer_below > 0) {
@@ -733,7 +733,21 @@ void run_count(Scratch& s, const PointSet& qs, const PointSet& bs, int C, int E,
     }
   }
   a.cnt_s = out.s; a.cnt_e0 = out.e0; a.cnt_e1 = out.e1; a.pairs = pairs;
-  CU(launch_count(C, E, qs.qpt, a, ts.count, s.c.stream));
+  // Few tiles for the GPU (N = 2*10^5: 800 CTAs of very different lengths on 592 resident slots, the SMs idle half of
+  // the launch): the chunk range of every tile is dealt to `split` CTAs that add their integer counts (exact, order-free)
+  a.split = 1;
+  if (a.prune_b_row >= 0 || a.cell_lo) {
+    const int64_t want = static_cast<int64_t>(s.c.sm_count) * 24;
+    a.split = static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(1, want / std::max(1, ts.count))));
+  }
+  if (const char* e = getenv("EB2_COUNT_SPLIT")) a.split = std::max(1, std::min(8, atoi(e)));     // tuning knob
+  if (a.split > 1) {
+    const PointSet& qp = qs;
+    if (out.s) CU(cudaMemsetAsync(out.s, 0, sizeof(int) * qp.stride, s.c.stream));
+    if (out.e0) CU(cudaMemsetAsync(out.e0, 0, sizeof(int) * qp.stride, s.c.stream));
+    if (out.e1) CU(cudaMemsetAsync(out.e1, 0, sizeof(int) * qp.stride, s.c.stream));
+  }
+  CU(launch_count(C, E, qs.qpt, a, ts.count * a.split, s.c.stream));
   s.launches++;
 }
 
