@@ -404,3 +404,28 @@ def test_walk_variants_agree_in_wider_spaces(monkeypatch):
                     m.setenv(key, val)
                 _, got = nat.entropy(coords, k, details=True)
             assert np.array_equal(got["dist"], ref["dist"]), (dims, env)
+
+
+def test_count_work_splitting_is_exact(monkeypatch):
+    """The fused Frenzel-Pompe / Ross counts with the chunk range of every tile dealt to 1, 2, 3 or 8 CTAs that add their
+    counts (EB2_COUNT_SPLIT; the default picks 1 to 4 from the number of tiles): the same three counts, bit for bit."""
+    rng = np.random.default_rng(31)
+    n = 70_000
+    z = rng.standard_t(3, size=(n, 3)); x = rng.normal(size=n) + z[:, 0]; y = 0.5 * x + z[:, 1] + rng.normal(size=n)
+    co = nat.pack_coords([x, y, z])
+    brute = nat.FLAG_NO_PRUNE | nat.FLAG_BRUTE_COUNT
+    v_ref, ref = nat.cmi(co, 3, flags=brute, details=True)
+    yd = rng.integers(0, 7, n)
+    cls, ncls = classes(yd)
+    cr = nat.pack_coords([x, z[:, :2]])
+    vr_ref, rref = nat.ross_cmi(cr, cls, ncls, 3, flags=brute, details=True)
+    for split in ("1", "2", "3", "8", None):
+        with monkeypatch.context() as m:
+            if split is not None:
+                m.setenv("EB2_COUNT_SPLIT", split)
+            v, got = nat.cmi(co, 3, details=True)
+            vr, rgot = nat.ross_cmi(cr, cls, ncls, 3, details=True)
+        for key in ("eps", "nxz", "nyz", "nz"):
+            assert np.array_equal(got[key], ref[key]), (split, key)
+            assert np.array_equal(rgot[key], rref[key]), (split, "ross", key)
+        assert close(v, v_ref) and close(vr, vr_ref), split
