@@ -81,6 +81,10 @@ def _stress():
     yield "thin-sheet", np.column_stack((rng.uniform(size=20_000), rng.uniform(size=20_000), 1e-6 * rng.normal(size=20_000)))
     yield "constant-coordinate", np.column_stack((rng.normal(size=(15_000, 2)), np.full(15_000, 3.0), rng.normal(size=15_000)))
     yield "huge-offset", rng.normal(size=(20_000, 3)) * 1e12 + 1e15
+    # coordinate 0 (the bucket coordinate) tied: five values fit the buckets, a constant column overflows them and the
+    # call is repeated on the general path
+    yield "tied-bucket-coordinate", np.column_stack((rng.integers(0, 5, 30_000).astype(float), rng.normal(size=(30_000, 3))))
+    yield "constant-bucket-coordinate", np.column_stack((np.full(20_000, -1.5), rng.normal(size=(20_000, 2))))
 
 
 @pytest.mark.parametrize("case", list(_stress()), ids=lambda c: c[0])
