@@ -101,6 +101,23 @@ __device__ __forceinline__ void block_minmax(double& mn, double& mx, double* red
   __syncthreads();
 }
 
+// block-wide sums of three doubles (every thread gets them); red: 64 doubles of shared scratch, at most 16 warps
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(kFull, a, o);
+    b += __shfl_xor_sync(kFull, b, o);
+    c += __shfl_xor_sync(kFull, c, o);
+  }
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[16 + w] = b; red[32 + w] = c; }
+  __syncthreads();
+  a = red[0]; b = red[16]; c = red[32];
+  for (int i = 1; i < nw; ++i) { a += red[i]; b += red[16 + i]; c += red[32 + i]; }
+  __syncthreads();
+}
+
 // ---- colgrid 1: the bucket function from a sorted regular sample ------------------------------------------------
 // The S <= 4,096 sample values are ranked by counting, spread over the GPU: a CTA owns 32 samples (one per lane), its
 // eight warps each compare them with an eighth of all samples (every lane reads the same shared-memory word: a
@@ -877,6 +894,38 @@ __global__ void __launch_bounds__(kG3Threads) layout3_kernel(const Col* col0, co
     while (C1 * C1 > cells) --C1;
     C2 = C1;
   }
+  // The range the cells of a coordinate span: the bucket's [min, max] cut to mean +- 3.5 sd of its rows within 3 sd (three
+  // rounds of trimming) - heavy-tailed data would otherwise spend the cells on the range of a few outliers and leave its
+  // core in a handful of them.  Values outside fall into the end cells: lin_cell clamps, the map stays monotone, which is
+  // all that exactness needs (the row order inside a bucket, hence the last bits of these sums, differs from run to
+  // run: the cell geometry may, the results cannot).
+  auto robust_range = [&](int coord, double mn, double mx, double& lo, double& hi) {
+    lo = mn; hi = mx;
+    if (!(mx > mn) || !(mx - mn < d_inf())) return;
+    double tl = -d_inf(), th = d_inf(), mean = 0.0, sd = 0.0, cnt = 0.0;
+    for (int round = 0; round < 3; ++round) {
+      double c0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const double v = g.raw[coord][c.srow[off + i]];
+        if (v >= tl && v <= th) { const double u = v - mn; c0 += 1.0; s1 += u; s2 += u * u; }
+      }
+      block_sum3(c0, s1, s2, redd);
+      if (!(c0 >= 2.0)) return;
+      cnt = c0;
+      const double m1 = s1 / c0;
+      mean = mn + m1;
+      sd = sqrt(fmax(0.0, s2 / c0 - m1 * m1));
+      if (!(sd > 0.0) || !(sd < d_inf())) return;
+      tl = mean - 3.0 * sd; th = mean + 3.0 * sd;
+    }
+    if (cnt < 0.5 * (double)len) return;
+    const double l2 = fmax(mn, mean - 3.5 * sd), h2 = fmin(mx, mean + 3.5 * sd);
+    if (h2 > l2) { lo = l2; hi = h2; }
+  };
+  double lo1, hi1, lo2 = 0.0, hi2 = 0.0;
+  robust_range(1, mn1, mx1, lo1, hi1);
+  if (g.G >= 3) robust_range(2, mn2, mx2, lo2, hi2);
+  mn1 = lo1; mx1 = hi1; mn2 = lo2; mx2 = hi2;
   const double sc1 = (mx1 > mn1 && mx1 - mn1 < d_inf()) ? (double)C1 / (mx1 - mn1) : 0.0;
   const double sc2 = (g.G >= 3 && mx2 > mn2 && mx2 - mn2 < d_inf()) ? (double)C2 / (mx2 - mn2) : 0.0;
   if (threadIdx.x == 0) {
