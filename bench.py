@@ -132,6 +132,18 @@ def _timed(fn, reps=5):
     return best, out
 
 
+def _steady(call, nat, dev, reps=3):
+    """Device phase times of one native call in steady state: the call repeated, the fastest repetition's phases (the
+    first call of a new shape also sizes the lane's workspace)."""
+    best = None
+    for _ in range(reps):
+        part = call()
+        ph = nat.last_timing(dev)
+        if best is None or ph["total_ms"] < best[1]["total_ms"]:
+            best = (part, ph)
+    return best
+
+
 def other_configs(nat, eb, dev, with_cpu):
     """BASELINE.json configs[0], [2], [4]: wall time of the public API call on host arrays (best of 5), device phase
     times of the estimator, the work done against the FP64 issue peak, and - on a bounded sample - the reference's
@@ -171,8 +183,7 @@ def other_configs(nat, eb, dev, with_cpu):
     lags = list(range(50))
     t_api, mi_l = _timed(lambda: eb.estimate_mi(y, x, lag=lags, k=K_NEIGH, cond=z), reps=2)
     co = nat.pack_coords([x, y, z])
-    part = nat.cmi_rows(co.ctypes.data, n, 3, K_NEIGH, 0, n, dev=dev)
-    ph = nat.last_timing(dev)
+    part, ph = _steady(lambda: nat.cmi_rows(co.ctypes.data, n, 3, K_NEIGH, 0, n, dev=dev), nat, dev)
     leg = {"workload": "estimate_mi(y, x, lag=range(50), k=3, cond=z) N=200,000, 3-D condition", "api_s": t_api,
            "api_ms_per_lag": t_api * 1e3 / len(lags), "mi_lag0": float(mi_l[0, 0]), "one_lag_phase_ms": ph,
            "roofline": roof(part[nat.P_PAIRS], 2 * 5, ph["knn_ms"] + ph["count_ms"], float(n) * n * 2)}
@@ -219,8 +230,7 @@ def other_configs(nat, eb, dev, with_cpu):
     d4 = rng.multivariate_normal(np.zeros(4), cov, size=n)
     t_api, h4 = _timed(lambda: float(eb.estimate_entropy(d4, k=5, multidim=True)), reps=3)
     co4 = nat.pack_coords([d4])
-    part = nat.entropy_rows(co4.ctypes.data, n, 4, 5, 0, n, dev=dev)
-    ph = nat.last_timing(dev)
+    part, ph = _steady(lambda: nat.entropy_rows(co4.ctypes.data, n, 4, 5, 0, n, dev=dev), nat, dev)
     leg = {"workload": "estimate_entropy(4-D Gaussian, k=5, multidim=True) N=500,000", "api_ms": t_api * 1e3, "entropy": h4,
            "phase_ms": ph, "roofline": roof(part[nat.P_PAIRS], 2 * 4, ph["knn_ms"], float(n) * n)}
     if with_cpu:

@@ -155,11 +155,41 @@ def _entropy_rows(rows: np.ndarray, k: int, mask, discrete: bool, drop_nan: bool
         rows = rows[~(np.max(bad, axis=1) if rows.ndim > 1 else bad)]
     if k >= rows.shape[0]:
         raise ValueError(_checks.MSG_K_TOO_LARGE)
+    if not discrete and _block_entropy_on_device(rows):
+        # a row-major (n, m) block goes up as it is (one copy, split into columns on the device) instead of being
+        # transposed on the host first; NaNs are found by the device's own scan of the data
+        try:
+            return _entropy_block_device(rows, k)
+        except _native.NonFiniteInput as e:
+            if e.nan:
+                raise ValueError(_checks.MSG_NANS_LEFT) from None
+            raise
     if not discrete and np.any(np.isnan(rows)):
         raise ValueError(_checks.MSG_NANS_LEFT)
     if discrete:
         return est._estimate_discrete_entropy(rows)
     return est._estimate_single_entropy(rows, k)
+
+
+def _block_entropy_on_device(rows: np.ndarray) -> bool:
+    if rows.ndim != 2 or rows.shape[1] < 2 or rows.dtype != np.float64 or rows.shape[0] < DEVICE_COLUMNS_MIN_ROWS:
+        return False
+    if _native.block_layout(rows) is None:
+        return False
+    from . import distributed
+    return not distributed.row_sharding_enabled()
+
+
+def _entropy_block_device(rows: np.ndarray, k: int) -> float:
+    dev = _devices.current()
+    store = _columns.ColumnStore()
+    try:
+        keys = store.add_columns(rows)
+        for key in keys:
+            store.ensure(dev, key)
+        return _native.entropy_cols([_native.ColDesc(key, 0, 1, 0.0, 0.0, 0, 0, 1) for key in keys], rows.shape[0], k, dev=dev)
+    finally:
+        store.close()
 
 
 def _entropy_of(x: np.ndarray, k: int, multidim: bool, mask, discrete: bool, drop_nan: bool):

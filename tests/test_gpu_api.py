@@ -336,8 +336,18 @@ def test_conditional_entropy_on_device_columns_gpu(monkeypatch):
     for j in range(3):
         want = oracle.knn_entropy(np.column_stack((x[:, j], c)), 3, backend="scipy")["value"] - h_c
         assert abs(dev[j] - want) <= 1e-10, j
+    # a multi-column variable without a condition: block upload + eb2_entropy_cols, the same bits as the host route
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host_block = eb.estimate_entropy(x, multidim=True, k=4)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 20_000)
+    assert eb.estimate_entropy(x, multidim=True, k=4) == host_block
+    assert abs(float(host_block) - oracle.knn_entropy(x, 4, backend="scipy")["value"]) <= 1e-10
     bad = x.copy(); bad[17, 2] = np.inf
     with pytest.raises(ValueError, match="data must be finite"):
         eb.estimate_entropy(bad, cond=c)
+    with pytest.raises(ValueError, match="data must be finite"):
+        eb.estimate_entropy(bad, multidim=True)
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_entropy(np.where(np.isinf(bad), np.nan, bad), multidim=True)
     with pytest.raises(ValueError, match="input contains NaNs"):
         eb.estimate_entropy(np.where(np.isinf(bad), np.nan, bad), cond=c)

@@ -375,8 +375,17 @@ def test_conditional_entropy_on_device_columns(oracle_backend, golden_api, monke
     assert eq(eb.estimate_entropy(x[:, 0], cond=c[:, 0], k=5), host_1d)
     x3, cond = g["inputs"]["x3"], g["inputs"]["cond"]
     assert eq(eb.estimate_entropy(x3[:, :2], cond=cond), g["ent_cond"]["out"])          # fixture of the unmodified reference
+    # a multi-column variable without a condition: the block goes up as it is, no host transposition
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host_block = eb.estimate_entropy(x, multidim=True, k=4)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    puts1 = oracle_backend.block_puts
+    assert eq(eb.estimate_entropy(x, multidim=True, k=4), host_block) and oracle_backend.block_puts == puts1 + 1
+    assert eq(eb.estimate_entropy(g["inputs"]["x3"], multidim=True, k=5), g["ent_multidim"]["out"])
     assert not oracle_backend.cache                                        # the store dropped its columns
     xn = x.copy(); xn[3, 1] = np.nan
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_entropy(xn, multidim=True)
     with pytest.raises(ValueError, match="input contains NaNs"):
         eb.estimate_entropy(xn, cond=c)
     with pytest.raises(ValueError, match="k must be smaller"):
