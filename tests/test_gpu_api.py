@@ -342,6 +342,12 @@ def test_conditional_entropy_on_device_columns_gpu(monkeypatch):
     monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 20_000)
     assert eb.estimate_entropy(x, multidim=True, k=4) == host_block
     assert abs(float(host_block) - oracle.knn_entropy(x, 4, backend="scipy")["value"]) <= 1e-10
+    # separate variables: one block upload, one estimate per cached column (1-D: the two-pointer k-NN kernel)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host_cols = eb.estimate_entropy(x, k=2)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 20_000)
+    assert np.array_equal(eb.estimate_entropy(x, k=2), host_cols)
+    assert abs(host_cols[1] - oracle.knn_entropy(x[:, 1], 2, backend="scipy")["value"]) <= 1e-10
     bad = x.copy(); bad[17, 2] = np.inf
     with pytest.raises(ValueError, match="data must be finite"):
         eb.estimate_entropy(bad, cond=c)

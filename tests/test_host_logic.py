@@ -382,8 +382,17 @@ def test_conditional_entropy_on_device_columns(oracle_backend, golden_api, monke
     puts1 = oracle_backend.block_puts
     assert eq(eb.estimate_entropy(x, multidim=True, k=4), host_block) and oracle_backend.block_puts == puts1 + 1
     assert eq(eb.estimate_entropy(g["inputs"]["x3"], multidim=True, k=5), g["ent_multidim"]["out"])
+    # separate variables (columns of a 2-D x): one block upload, one estimate per cached column
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 10 ** 9)
+    host_cols = eb.estimate_entropy(x, k=2)
+    monkeypatch.setattr(api, "DEVICE_COLUMNS_MIN_ROWS", 0)
+    puts2 = oracle_backend.block_puts
+    assert eq(eb.estimate_entropy(x, k=2), host_cols) and oracle_backend.block_puts == puts2 + 1
+    assert eq(eb.estimate_entropy(g["inputs"]["x3"]), g["ent_cols"]["out"])
     assert not oracle_backend.cache                                        # the store dropped its columns
     xn = x.copy(); xn[3, 1] = np.nan
+    with pytest.raises(ValueError, match="input contains NaNs"):
+        eb.estimate_entropy(xn)
     with pytest.raises(ValueError, match="input contains NaNs"):
         eb.estimate_entropy(xn, multidim=True)
     with pytest.raises(ValueError, match="input contains NaNs"):
