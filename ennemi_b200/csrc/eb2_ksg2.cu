@@ -1568,9 +1568,10 @@ Plan make_plan3(int64_t n, int D, bool* ok) {
   (void)D;
   Plan p;
   p.n = n;
-  // buckets of ~2,048 rows (C1 x C2 = 45 x 45 cells; a quarter of what a bucket may hold: the quantile estimates from 8
-  // samples per bucket scatter by +-35 %): in three and more dimensions a k-th neighbour distance spans several buckets anyway
-  int64_t rows = 2048;
+  // buckets of ~3,072 rows (C1 x C2 = 55 x 55 cells; three eighths of what a bucket may hold: with up to 32 samples per
+  // splitter the bucket sizes scatter by ~20 %): in three and more dimensions a k-th neighbour distance spans several
+  // buckets anyway.  Measured with the window limit of knn3 (4-D, N = 5*10^5): 2,048 rows / 256 cells 8.45 ms, 3,072 / 512 7.84 ms
+  int64_t rows = 3072;
   if (const char* e = getenv("EB2_G3_ROWS")) rows = atoll(e);           // tuning knob
   if (rows < 256) rows = 256;
   if (rows > kBucketCap / 2) rows = kBucketCap / 2;
@@ -1641,7 +1642,7 @@ cudaError_t layout3(const Col* col0, const Grid3* g, const Plan& p, cudaStream_t
 template <int D>
 static cudaError_t knn3_d(const Col* col0, const Grid3* g, const Plan& p, int k, int near, int sm_count, cudaStream_t s) {
   const int grid = static_cast<int>((p.n + kG3Threads - 1) / kG3Threads);
-  int heavy = 256;       // cells of one bucket's window a single thread still walks (the lanes of a warp are neighbours:
+  int heavy = 512;       // cells of one bucket's window a single thread still walks (the lanes of a warp are neighbours:
                          // their windows are alike)
   if (const char* e = getenv("EB2_G3_HEAVY")) heavy = atoi(e);        // tuning knob
   if (k + 1 <= 4) {
